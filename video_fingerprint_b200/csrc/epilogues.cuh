@@ -1,0 +1,172 @@
+// Epilogue functors for gemm_tcgen05_kernel. Each epilogue thread owns ONE accumulator row of the
+// 128-row tile and receives it in chunks of 32 consecutive fp32 columns straight from TMEM.
+#pragma once
+#include "sm100_primitives.cuh"
+
+namespace vfp {
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// -------------------------------------------------------------------------------------------
+// y = act(acc + bias [+ pe[pos[row]]]) [+ residual]  -> fp32 and/or bf16 row-major outputs
+// -------------------------------------------------------------------------------------------
+struct EpiBiasAct {
+  struct Params {
+    const float* bias;       // [N] or null
+    const float* residual;   // [M][ld_res] fp32 or null (added after the activation)
+    const float* pe;         // [max_len][N] positional table or null
+    const int* token_pos;    // [M] position of each row inside its clip (with pe)
+    float* out_f32;          // [M][ld_out] or null
+    __nv_bfloat16* out_bf16; // [M][ld_out] or null
+    int ld_res, ld_out;
+    int M, N;
+    int act;  // 0 none, 1 relu, 2 gelu(erf)
+  };
+  __device__ __forceinline__ void begin(const Params&, int, int, int) {}
+  __device__ __forceinline__ void end(const Params&, int, int, int) {}
+  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32]) {
+    const long long grow = (long long)mt * kBlockMRows + row;
+    if (grow >= p.M || col0 >= p.N) return;
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+    if (p.bias) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+        x[i] += b.x; x[i + 1] += b.y; x[i + 2] += b.z; x[i + 3] += b.w;
+      }
+    }
+    if (p.pe) {
+      const float* pr = p.pe + (long long)p.token_pos[grow] * p.N + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(pr + i));
+        x[i] += b.x; x[i + 1] += b.y; x[i + 2] += b.z; x[i + 3] += b.w;
+      }
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
+    } else if (p.act == 2) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = gelu_erf(x[i]);
+    }
+    if (p.residual) {
+      const float* rr = p.residual + grow * p.ld_res + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(rr + i);
+        x[i] += b.x; x[i + 1] += b.y; x[i + 2] += b.z; x[i + 3] += b.w;
+      }
+    }
+    if (p.out_f32) {
+      float* o = p.out_f32 + grow * p.ld_out + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(x[i], x[i + 1], x[i + 2], x[i + 3]);
+    }
+    if (p.out_bf16) {
+      __nv_bfloat16* o = p.out_bf16 + grow * p.ld_out + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        uint4 q;
+        q.x = pack_bf16x2(x[i], x[i + 1]);
+        q.y = pack_bf16x2(x[i + 2], x[i + 3]);
+        q.z = pack_bf16x2(x[i + 4], x[i + 5]);
+        q.w = pack_bf16x2(x[i + 6], x[i + 7]);
+        *reinterpret_cast<uint4*>(o + i) = q;
+      }
+    }
+  }
+  static constexpr int kBlockMRows = 128;
+};
+
+// -------------------------------------------------------------------------------------------
+// conv4 epilogue: relu(acc + bias), then the 4x4 global average pool. A tile holds 8 frames x 16
+// pixels, so each half-warp (16 lanes) is exactly one frame; a halving butterfly leaves lane j of
+// the half-warp with the sums of columns 2j, 2j+1 of the chunk.
+// -------------------------------------------------------------------------------------------
+struct EpiConvPool16 {
+  struct Params {
+    const float* bias;        // [N]
+    __nv_bfloat16* out_bf16;  // [frames][N]
+    int frames, N;
+  };
+  __device__ __forceinline__ void begin(const Params&, int, int, int) {}
+  __device__ __forceinline__ void end(const Params&, int, int, int) {}
+  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+      x[i] = fmaxf(__uint_as_float(v[i]) + b.x, 0.0f);
+      x[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.0f);
+      x[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.0f);
+      x[i + 3] = fmaxf(__uint_as_float(v[i + 3]) + b.w, 0.0f);
+    }
+#pragma unroll
+    for (int half = 16, bit = 8; half >= 2; half >>= 1, bit >>= 1) {
+      const bool upper = (lane & bit) != 0;
+#pragma unroll
+      for (int i = 0; i < half; ++i) {
+        const float keep = upper ? x[i + half] : x[i];
+        const float send = upper ? x[i] : x[i + half];
+        x[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+      }
+    }
+    const long long frame = (long long)mt * 8 + (row >> 4);
+    if (frame < p.frames) {
+      const int c = col0 + 2 * (lane & 15);
+      *reinterpret_cast<uint32_t*>(p.out_bf16 + frame * p.N + c) = pack_bf16x2(x[0] * 0.0625f, x[1] * 0.0625f);
+    }
+  }
+};
+
+// -------------------------------------------------------------------------------------------
+// similarity-join screen: emit (i, j, s) for every accumulator >= thr (bf16 inputs, fp32 accumulate).
+// Survivors are rare, so one global atomic per hit is cheaper than any staging. `count` keeps
+// counting past `capacity` so the caller can size a retry.
+// -------------------------------------------------------------------------------------------
+struct EpiJoinThreshold {
+  struct Params {
+    float thr;
+    long long q_rows, db_rows;  // valid extents
+    long long q_row0;           // global index of local query row 0 (row-block shard offset)
+    int* out_i;
+    int* out_j;
+    float* out_s;
+    unsigned long long* count;
+    long long capacity;
+  };
+  __device__ __forceinline__ void begin(const Params&, int, int, int) {}
+  __device__ __forceinline__ void end(const Params&, int, int, int) {}
+  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32]) {
+    const long long qi = (long long)mt * 128 + row;
+    if (qi >= p.q_rows) return;
+    float m = __uint_as_float(v[0]);
+#pragma unroll
+    for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
+    if (!(m >= p.thr)) return;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const float s = __uint_as_float(v[i]);
+      const long long j = (long long)col0 + i;
+      if (s >= p.thr && j < p.db_rows) {
+        const unsigned long long slot = atomicAdd(p.count, 1ull);
+        if ((long long)slot < p.capacity) {
+          p.out_i[slot] = (int)(p.q_row0 + qi);
+          p.out_j[slot] = (int)j;
+          p.out_s[slot] = s;
+        }
+      }
+    }
+  }
+};
+
+}  // namespace vfp

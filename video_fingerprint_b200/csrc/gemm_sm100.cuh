@@ -1,0 +1,203 @@
+// Persistent, warp-specialised tcgen05 GEMM skeleton for sm_100a.
+//
+//   D[128 x BLOCK_N] (fp32, TMEM) = A[128 x K] (bf16, K-major) * B[BLOCK_N x K]^T (bf16, K-major)
+//
+//   warp 0      : TMA producer (one lane)            global -> swizzled smem ring, mbarrier complete_tx
+//   warp 1      : TMEM allocator + UMMA issuer (one lane), tcgen05.commit releases smem stages
+//   warps 2..5  : epilogue; each warp owns one 32-lane quarter of the 128 accumulator rows and
+//                 drains them with tcgen05.ld while the issuer already fills the other accumulator
+//                 buffer (two BLOCK_N-column buffers in TMEM).
+//
+// The A operand is fetched either as a plain 2-D row tile or as a strided 4-D box over an NHWC
+// activation tensor (one 3x3/stride-2 filter tap per K block = implicit-GEMM convolution with the
+// im2col done by the TMA unit, padding supplied by its out-of-bounds zero fill).
+#pragma once
+#include "sm100_primitives.cuh"
+
+namespace vfp {
+
+constexpr int kGemmThreads = 192;
+constexpr int kBlockM = 128;
+
+struct GemmShape {
+  int m_tiles;     // number of 128-row tiles
+  int n_tiles;     // number of BLOCK_N column tiles
+  int k_blocks;    // K / BLOCK_K
+  int group_m;     // rasterisation: tiles are walked in groups of `group_m` row tiles (L2 reuse)
+  // A operand addressing
+  int a_conv;           // 0: rows are GEMM rows; 1: 4-D strided box (C, W, H, frame)
+  int tiles_per_frame;  // conv: row tiles per frame (>=1) ...
+  int frames_per_tile;  //       ... or frames per row tile (>=1)
+  int tile_out_rows;    // conv: output rows (H) covered by one tile inside a frame
+  int cblocks_per_tap;  // conv: K blocks per filter tap (C_in / BLOCK_K)
+};
+
+__device__ __forceinline__ void tile_coords(const GemmShape& s, int t, int& mt, int& nt) {
+  const int group_size = s.group_m * s.n_tiles;
+  const int g = t / group_size;
+  const int r = t - g * group_size;
+  const int m_first = g * s.group_m;
+  const int gm = min(s.group_m, s.m_tiles - m_first);
+  mt = m_first + (r % gm);
+  nt = r / gm;
+}
+
+template <int BLOCK_N, int BLOCK_K, int STAGES>
+struct GemmSmemLayout {
+  static constexpr int kRowBytes = BLOCK_K * 2;
+  static constexpr int kABytes = kBlockM * kRowBytes;
+  static constexpr int kBBytes = BLOCK_N * kRowBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024 /*alignment slack*/;
+};
+
+template <int BLOCK_N, int BLOCK_K, int STAGES, class Epilogue>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                    const GemmShape shape, const typename Epilogue::Params ep) {
+  using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES>;
+  static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
+  static_assert(BLOCK_K == 64 || BLOCK_K == 32 || BLOCK_K == 16, "BLOCK_K");
+  constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                 : (2 * BLOCK_N <= 256) ? 256 : 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * L::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* acc_full = bars + 2 * STAGES;     // [2]
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = shape.m_tiles * shape.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mt, nt;
+        tile_coords(shape, t, mt, nt);
+        int frame0 = 0, oh0 = 0;
+        if (shape.a_conv) {
+          if (shape.tiles_per_frame > 1) {
+            frame0 = mt / shape.tiles_per_frame;
+            oh0 = (mt - frame0 * shape.tiles_per_frame) * shape.tile_out_rows;
+          } else {
+            frame0 = mt * shape.frames_per_tile;
+          }
+        }
+        for (int kb = 0; kb < shape.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
+          if (shape.a_conv) {
+            const int tap = kb / shape.cblocks_per_tap;
+            const int cb = kb - tap * shape.cblocks_per_tap;
+            const int kh = tap / 3, kw = tap - kh * 3;
+            tma_load_4d(&tmap_a, &full_bar[stage], smem_a + stage * L::kABytes, cb * BLOCK_K, kw - 1,
+                        2 * oh0 + kh - 1, frame0);
+          } else {
+            tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * L::kABytes, kb * BLOCK_K, mt * kBlockM);
+          }
+          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * L::kBBytes, kb * BLOCK_K, nt * BLOCK_N);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ UMMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < shape.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc_kmajor<L::kRowBytes>(smem_u32(smem_a + stage * L::kABytes));
+          const uint64_t bdesc = umma_smem_desc_kmajor<L::kRowBytes>(smem_u32(smem_b + stage * L::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advancing 16 bf16 along K = 32 bytes = 2 units of the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
+    const int row = quarter * 32 + lane;
+    int local = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      int mt, nt;
+      tile_coords(shape, t, mt, nt);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      Epilogue epi;
+      epi.begin(ep, mt, nt, row);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + c, v);
+        tmem_ld_wait();
+        epi.chunk(ep, mt, nt * BLOCK_N + c, row, v);
+      }
+      epi.end(ep, mt, nt, row);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace vfp

@@ -1,0 +1,71 @@
+// Host-side CUtensorMap construction. The driver entry point is resolved through the runtime
+// (cudaGetDriverEntryPoint), so the library carries no link-time dependency on libcuda.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace vfp {
+
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                             const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                             CUtensorMapFloatOOBfill);
+
+inline PFN_tensorMapEncodeTiled tensor_map_encoder() {
+  static PFN_tensorMapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !p) {
+      return nullptr;
+    }
+    fn = reinterpret_cast<PFN_tensorMapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+inline CUtensorMapSwizzle swizzle_for_row_bytes(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+         : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+         : row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                           : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+
+// bf16 matrix [rows][cols] with row pitch `ld` elements; box = box_rows x box_cols (cols innermost).
+inline int make_tmap_rows_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                               uint32_t box_rows, uint32_t box_cols) {
+  PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(box_cols * 2),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+// bf16 NHWC activation tensor [frames][H][W][C] read as the A operand of a 3x3 / stride-2 / pad-1
+// convolution: one box = (c_box channels) x (out_w outputs along W, every 2nd pixel) x (out_h outputs
+// along H, every 2nd pixel) x (n_box frames). Out-of-range coordinates (the -1 halo, frames past the
+// end) are zero-filled by the TMA unit.
+inline int make_tmap_conv_s2_bf16(CUtensorMap* out, const void* base, uint64_t frames, uint32_t H, uint32_t W,
+                                  uint32_t C, uint32_t c_box, uint32_t out_w, uint32_t out_h, uint32_t n_box) {
+  PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  cuuint64_t gdim[4] = {C, W, H, frames};
+  cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {c_box, out_w * 2, out_h * 2, n_box};
+  cuuint32_t estr[4] = {1, 2, 2, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(c_box * 2),
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+}  // namespace vfp
