@@ -1,0 +1,110 @@
+/*
+ * vfp_b200 - C ABI of the B200 (sm_100a) duplicate-detection hot path.
+ *
+ * The reference (Alexandre-nk-Perdereau/video-fingerprint) has no FFI layer: its hot path is two Python
+ * call sites. Each entry point below replaces the device work behind one of them; the Python host layer in
+ * video_fingerprint_b200/ mirrors the reference call signatures and calls these through ctypes
+ * (see INTEGRATION.md for the binding a reference maintainer would add).
+ *
+ *   reference call site                                   replaced by
+ *   ----------------------------------------------------  -------------------------------------------
+ *   model.load_state_dict(...)      fingerprint.py:70     vfp_weights_create  (BN folding, bf16 packing)
+ *   self.model(clip)                fingerprint.py:248    vfp_forward
+ *     = VideoFingerprintAttention.forward  model.py:272-298
+ *   np.dot(E, E.T) + np.where(>=)   fingerprint.py:493-499  vfp_join_threshold
+ *   faiss IndexFlatIP.add/search    fingerprint.py:524-528  vfp_topk_ip
+ *
+ * Conventions: plain C types only; every buffer is caller-owned; `stream` is a CUDA stream handle
+ * (cudaStream_t / CUstream) passed as void*; all device pointers belong to the current device; calls
+ * are asynchronous on `stream` and re-entrant (no global mutable state besides the last-error string,
+ * which is thread-local). Return value 0 = success, nonzero = error (message via vfp_last_error()).
+ * There is no CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef VFP_B200_H_
+#define VFP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VFP_ABI_VERSION 1
+
+/* frame element types accepted by vfp_forward (planar (T,3,64,64) frames as produced by
+ * _preprocess_frames, fingerprint.py:186-214; U8 values are scaled by 1/255 on the device) */
+#define VFP_FRAME_U8 0
+#define VFP_FRAME_BF16 1
+#define VFP_FRAME_F32 2
+
+typedef struct vfp_weights vfp_weights;
+
+/* One entry of the reference checkpoint's model_state_dict (model.py:97-118,129-138,160-175,195-226):
+ * `name` is the state_dict key, `data` a HOST pointer to contiguous fp32 values (int64 for
+ * num_batches_tracked entries, which are ignored), `numel` the element count. */
+typedef struct {
+  const char* name;
+  const void* data;
+  int64_t numel;
+} vfp_tensor_desc;
+
+int vfp_abi_version(void);
+const char* vfp_last_error(void);
+
+/* Number of SMs of the current device (also a cheap "is there a GPU" probe). Returns <= 0 on failure. */
+int vfp_device_sm_count(void);
+
+/* Build the device-resident inference weights from the 144 checkpoint tensors: eval-mode BatchNorm is
+ * folded into the preceding conv, Linear(256->S) o Linear(S->256) is folded into one 256x256 map,
+ * GEMM operands are packed to bf16 K-major. Blocks until the upload has finished. */
+int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weights** out);
+void vfp_weights_destroy(vfp_weights* w);
+/* embedding_dim of the loaded checkpoint (final_projection.3 rows). */
+int vfp_weights_embedding_dim(const vfp_weights* w);
+
+/* Device workspace needed to push `frames_per_pass` frames (and up to `clips_per_pass` clips) through
+ * the network in one pass. vfp_forward splits its input into passes that fit the workspace it is given;
+ * the minimum useful value is the longest clip. */
+size_t vfp_forward_workspace_bytes(int64_t frames_per_pass, int64_t clips_per_pass);
+
+/* Fingerprint `n_clips` clips. `frames` is the packed device tensor (sum T, 3, 64, 64) of type
+ * `frame_dtype`; `cu_seqlens_host` holds n_clips+1 int32 prefix sums of the clip lengths (HOST memory).
+ * Writes unit-norm embeddings (n_clips, D) fp32 to `emb_out` (device). If `features_out` is non-null it
+ * receives the temporal features (sum T, 256) fp32 (forward(..., return_features=True), model.py:296-297).
+ * Each clip is treated exactly like a B=1 call of the reference module (fingerprint.py:244-249). */
+int vfp_forward(const vfp_weights* w, const void* frames, int frame_dtype, const int32_t* cu_seqlens_host,
+                int n_clips, float* emb_out, float* features_out, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* All-pairs cosine/inner-product threshold join of a query row block against a database:
+ * emits every (i, j, s) with s = <q_i, db_j> >= thr computed in fp32, i = q_row0 + local row (so a
+ * row-block shard reports global indices). `q`/`db` are device fp32 (n, dim) row-major, dim == 256.
+ * `screen_margin` must be >= 2^-8 * max|q_i| * max|db_j| (0.004 for unit vectors): the tensor-core
+ * screen runs in bf16 at thr - screen_margin and survivors are re-scored in fp32.
+ * counts_out (device, 2 x uint64): [0] = number of result pairs (may exceed `capacity`; only the first
+ * `capacity` are stored, in no particular order), [1] = number of screen candidates (if it exceeds the
+ * candidate capacity implied by the workspace the result is incomplete and the caller must retry with
+ * the workspace vfp_join_workspace_bytes(..., candidates) reports). */
+size_t vfp_join_workspace_bytes(int64_t n_q, int64_t n_db, int64_t candidate_capacity);
+int vfp_join_threshold(const float* q, const float* db, int64_t n_q, int64_t n_db, int dim, int64_t q_row0,
+                       float thr, float screen_margin, int32_t* out_i, int32_t* out_j, float* out_s,
+                       int64_t capacity, uint64_t* counts_out, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* Exact flat inner-product top-k (the arithmetic of faiss.IndexFlatIP.search): for every query row the k
+ * largest <q_i, db_j> in fp32, sorted by (score descending, index ascending). out_s (n_q, k) fp32,
+ * out_idx (n_q, k) int64, device memory. k <= 32. `flags_out` (device, 1 x uint64) counts query rows whose
+ * exactness could not be proven by the bf16 screen bound and were recomputed by the fp32 fallback. */
+size_t vfp_topk_workspace_bytes(int64_t n_q, int64_t n_db, int k);
+int vfp_topk_ip(const float* q, const float* db, int64_t n_q, int64_t n_db, int dim, int k,
+                float screen_margin, float* out_s, int64_t* out_idx, uint64_t* flags_out, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* Reads and clears the device-side error word set by a kernel watchdog (0 = none). Synchronises. */
+unsigned int vfp_device_error_word(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFP_B200_H_ */

@@ -1,0 +1,33 @@
+"""video_fingerprint_b200 - B200 (sm_100a) implementation of the video-fingerprint duplicate-detection hot path.
+
+Public surface (mirrors /root/reference/model.py and /root/reference/fingerprint.py for the hot path only):
+
+    create_model, VideoFingerprintAttention          reference model factory / module (state_dict compatible)
+    VideoFingerprintScanner                          find_duplicates / save_results / per-video semantics
+    threshold_join, topk_inner_product               the two similarity-search primitives
+    sharding                                         multi-GPU partitioning + NCCL all-gather join
+
+All device work goes through libvfp_b200.so (include/vfp_b200.h); there is no CPU or PyTorch fallback.
+"""
+from .model import VideoFingerprintAttention, create_model  # noqa: F401
+from .fingerprint import (  # noqa: F401
+    VideoFingerprintScanner,
+    group_pairs_direct,
+    group_pairs_topk,
+    threshold_join,
+    threshold_join_device,
+    topk_inner_product,
+    topk_inner_product_device,
+)
+
+__all__ = [
+    "create_model",
+    "VideoFingerprintAttention",
+    "VideoFingerprintScanner",
+    "threshold_join",
+    "threshold_join_device",
+    "topk_inner_product",
+    "topk_inner_product_device",
+    "group_pairs_direct",
+    "group_pairs_topk",
+]

@@ -1,0 +1,140 @@
+// Frame-encoder stem: Conv2d(3->32, k5, s2, p2) + folded BatchNorm + ReLU, planar CHW frames in
+// (u8 / bf16 / fp32), bf16 NHWC [frame][32][32][32] out.
+//
+// C_in = 3 gives 6-byte pixels, which neither the TMA im2col box nor a UMMA smem descriptor can address,
+// so this layer runs on the register-fragment tensor path (mma.sync m16n8k16, bf16 -> fp32): every thread
+// builds its A fragments straight from an HWC copy of the frame in shared memory. The GEMM view is
+//   M = 1024 output pixels, N = 32, K = 5 (kh) x 16 (15 = 5 kw x 3 c, +1 zero-weight pad).
+// For output pixel (oh, ow) and filter row kh the 15 taps are 15 CONSECUTIVE bf16 values of the padded HWC
+// frame, so each A register (two consecutive k) is one aligned 32-bit shared load.
+#pragma once
+#include "sm100_primitives.cuh"
+
+namespace vfp {
+
+constexpr int kC1Threads = 256;
+constexpr int kC1PadW = 68;   // columns -2 .. 65
+constexpr int kC1PadH = 67;   // rows    -2 .. 64
+constexpr int kC1SmemElems = kC1PadH * kC1PadW * 3 + 8;
+
+enum FrameDtype : int { kFrameU8 = 0, kFrameBF16 = 1, kFrameF32 = 2 };
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// wpack: [5 kh][4 n-tiles][32 lanes][2] packed bf16x2 B fragments, bias: [32] fp32 (BN folded)
+__global__ void __launch_bounds__(kC1Threads)
+conv1_stem_kernel(const void* __restrict__ frames, int frame_dtype, long long n_frames,
+                  const uint32_t* __restrict__ wpack, const float* __restrict__ bias,
+                  __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) __nv_bfloat16 tile[kC1SmemElems];
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, tig = lane & 3;
+
+  // B fragments and bias stay in registers for the whole kernel.
+  uint32_t bfrag[5][4][2];
+#pragma unroll
+  for (int kh = 0; kh < 5; ++kh)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(wpack) + (kh * 4 + nt) * 32 + lane);
+      bfrag[kh][nt][0] = w.x;
+      bfrag[kh][nt][1] = w.y;
+    }
+  float bia[4][2];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    bia[nt][0] = __ldg(bias + nt * 8 + 2 * tig);
+    bia[nt][1] = __ldg(bias + nt * 8 + 2 * tig + 1);
+  }
+
+  // zero the halo once: interior cells are rewritten for every frame, halo cells never are.
+  for (int i = tid; i < kC1SmemElems; i += kC1Threads) tile[i] = __float2bfloat16(0.0f);
+  __syncthreads();
+
+  for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
+    // ---- stage the frame: planar CHW -> padded HWC bf16 ----
+    if (frame_dtype == kFrameU8) {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(frames) + f * 12288);
+      for (int i = tid; i < 3072; i += kC1Threads) {
+        const uint32_t q = __ldg(src + i);
+        const int e = i * 4;
+        const int c = e >> 12, h = (e >> 6) & 63, w = e & 63;
+        __nv_bfloat16* d = tile + ((h + 2) * kC1PadW + (w + 2)) * 3 + c;
+        d[0] = __float2bfloat16((float)(q & 0xFF) * (1.0f / 255.0f));
+        d[3] = __float2bfloat16((float)((q >> 8) & 0xFF) * (1.0f / 255.0f));
+        d[6] = __float2bfloat16((float)((q >> 16) & 0xFF) * (1.0f / 255.0f));
+        d[9] = __float2bfloat16((float)(q >> 24) * (1.0f / 255.0f));
+      }
+    } else if (frame_dtype == kFrameBF16) {
+      const uint2* src = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(frames) + f * 12288);
+      for (int i = tid; i < 3072; i += kC1Threads) {
+        const uint2 q = __ldg(src + i);
+        const int e = i * 4;
+        const int c = e >> 12, h = (e >> 6) & 63, w = e & 63;
+        __nv_bfloat16* d = tile + ((h + 2) * kC1PadW + (w + 2)) * 3 + c;
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+        d[0] = lo.x; d[3] = lo.y; d[6] = hi.x; d[9] = hi.y;
+      }
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(frames) + f * 12288);
+      for (int i = tid; i < 3072; i += kC1Threads) {
+        const float4 q = __ldg(src + i);
+        const int e = i * 4;
+        const int c = e >> 12, h = (e >> 6) & 63, w = e & 63;
+        __nv_bfloat16* d = tile + ((h + 2) * kC1PadW + (w + 2)) * 3 + c;
+        d[0] = __float2bfloat16(q.x); d[3] = __float2bfloat16(q.y);
+        d[6] = __float2bfloat16(q.z); d[9] = __float2bfloat16(q.w);
+      }
+    }
+    __syncthreads();
+
+    // ---- 64 m-tiles of 16 pixels; warp w takes m-tiles w, w+8, ... ----
+    const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
+    __nv_bfloat16* out_f = out + f * (1024 * 32);
+#pragma unroll 2
+    for (int mt = warp; mt < 64; mt += 8) {
+      const int oh = mt >> 1;
+      const int ow0 = (mt & 1) * 16;
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
+#pragma unroll
+      for (int kh = 0; kh < 5; ++kh) {
+        // element offset of (pixel ow, k) = ((2*oh+kh)*PadW + 2*ow)*3 + k ; all terms even -> word aligned
+        const int base_lo = (((2 * oh + kh) * kC1PadW + 2 * (ow0 + g)) * 3) >> 1;
+        const int base_hi = base_lo + 24;  // pixel +8 -> +16 columns -> +48 elements -> +24 words
+        uint32_t a[4];
+        a[0] = tile32[base_lo + tig];
+        a[1] = tile32[base_hi + tig];
+        a[2] = tile32[base_lo + tig + 4];
+        a[3] = tile32[base_hi + tig + 4];
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a, bfrag[kh][nt]);
+      }
+      const int p_lo = oh * 32 + ow0 + g;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float v0 = fmaxf(acc[nt][0] + bia[nt][0], 0.0f);
+        const float v1 = fmaxf(acc[nt][1] + bia[nt][1], 0.0f);
+        const float v2 = fmaxf(acc[nt][2] + bia[nt][0], 0.0f);
+        const float v3 = fmaxf(acc[nt][3] + bia[nt][1], 0.0f);
+        __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1);
+        __nv_bfloat162 hi = __floats2bfloat162_rn(v2, v3);
+        *reinterpret_cast<__nv_bfloat162*>(out_f + p_lo * 32 + nt * 8 + 2 * tig) = lo;
+        *reinterpret_cast<__nv_bfloat162*>(out_f + (p_lo + 8) * 32 + nt * 8 + 2 * tig) = hi;
+      }
+    }
+    __syncthreads();  // before the next frame overwrites the tile
+  }
+}
+
+}  // namespace vfp

@@ -1,0 +1,667 @@
+// C-ABI implementation (include/vfp_b200.h): weight preparation, forward orchestration, similarity join.
+// Single translation unit: all kernels are included as headers so the library is one nvcc invocation.
+#include "../../include/vfp_b200.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "conv1_kernel.cuh"
+#include "gemm_launch.cuh"
+#include "join_kernels.cuh"
+#include "token_kernels.cuh"
+#include "topk_kernels.cuh"
+
+using namespace vfp;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(const std::string& msg) {
+  g_last_error = msg;
+  return 1;
+}
+int fail_cuda(const char* what, cudaError_t e) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return 2;
+}
+#define VFP_CUDA(call)                                  \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) return fail_cuda(#call, e__); \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr float kBnEps = 1e-5f;
+const int kTemporalKernels[4] = {3, 5, 7, 11};
+
+struct AttnBlockWeights {
+  float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  __nv_bfloat16 *wqkv, *wo, *w1, *w2;
+  float *bqkv, *bo, *b1, *b2;
+  CUtensorMap tm_qkv, tm_o, tm_w1, tm_w2;
+};
+
+}  // namespace
+
+struct vfp_weights {
+  int embedding_dim = 0;
+  int n_attn = 0;
+  std::vector<void*> allocs;
+  // frame encoder
+  uint32_t* c1_wpack = nullptr;
+  float* c1_bias = nullptr;
+  __nv_bfloat16 *c2_w = nullptr, *c3_w = nullptr, *c4_w = nullptr;
+  float *c2_b = nullptr, *c3_b = nullptr, *c4_b = nullptr;
+  CUtensorMap tm_c2, tm_c3, tm_c4;
+  // token embedding (Linear 256->S o Linear S->256, folded) + positional table
+  __nv_bfloat16* wtok = nullptr;
+  float* btok = nullptr;
+  float* pe = nullptr;
+  int pe_len = 0;
+  CUtensorMap tm_tok;
+  // temporal conv blocks
+  float* tc_w[2] = {nullptr, nullptr};
+  float* tc_b[2] = {nullptr, nullptr};
+  std::vector<AttnBlockWeights> attn;
+  // pooling + head
+  __nv_bfloat16* wpool = nullptr;
+  float* bpool = nullptr;
+  CUtensorMap tm_pool;
+  float *w0t = nullptr, *b0 = nullptr, *w3t = nullptr, *b3 = nullptr;
+};
+
+namespace {
+
+struct TensorTable {
+  std::map<std::string, const vfp_tensor_desc*> by_name;
+  const float* get(const std::string& name, int64_t numel, std::string* err) const {
+    auto it = by_name.find(name);
+    if (it == by_name.end()) {
+      *err = "missing checkpoint tensor: " + name;
+      return nullptr;
+    }
+    if (it->second->numel != numel) {
+      *err = "checkpoint tensor " + name + " has " + std::to_string(it->second->numel) + " elements, expected " +
+             std::to_string(numel);
+      return nullptr;
+    }
+    return static_cast<const float*>(it->second->data);
+  }
+  bool has(const std::string& name) const { return by_name.count(name) != 0; }
+  int64_t numel(const std::string& name) const {
+    auto it = by_name.find(name);
+    return it == by_name.end() ? -1 : it->second->numel;
+  }
+};
+
+template <class T>
+int upload(vfp_weights* w, const std::vector<T>& host, T** dev) {
+  void* p = nullptr;
+  VFP_CUDA(cudaMalloc(&p, host.size() * sizeof(T)));
+  w->allocs.push_back(p);
+  VFP_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dev = static_cast<T*>(p);
+  return 0;
+}
+
+std::vector<__nv_bfloat16> to_bf16(const std::vector<float>& v) {
+  std::vector<__nv_bfloat16> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = __float2bfloat16(v[i]);
+  return o;
+}
+
+// eval-mode BN as per-channel scale/shift:  y = (x - mean) * gamma / sqrt(var + eps) + beta
+struct BnFold {
+  std::vector<float> scale, shift;
+};
+bool load_bn(const TensorTable& t, const std::string& prefix, int c, BnFold* out, std::string* err) {
+  const float* g = t.get(prefix + ".weight", c, err);
+  const float* b = g ? t.get(prefix + ".bias", c, err) : nullptr;
+  const float* m = b ? t.get(prefix + ".running_mean", c, err) : nullptr;
+  const float* v = m ? t.get(prefix + ".running_var", c, err) : nullptr;
+  if (!v) return false;
+  out->scale.resize(c);
+  out->shift.resize(c);
+  for (int i = 0; i < c; ++i) {
+    const double s = (double)g[i] / sqrt((double)v[i] + (double)kBnEps);
+    out->scale[i] = (float)s;
+    out->shift[i] = (float)((double)b[i] - (double)m[i] * s);
+  }
+  return true;
+}
+
+// 3x3 conv weights (cout, cin, 3, 3) -> K-major GEMM operand [cout][(kh*3+kw)*cin + c], BN folded
+int prep_conv3x3(vfp_weights* w, const TensorTable& t, int conv_idx, int cin, int cout, __nv_bfloat16** dw, float** db,
+                 std::string* err) {
+  const std::string p = "spatial_encoder.encoder.";
+  const float* cw = t.get(p + std::to_string(conv_idx) + ".weight", (int64_t)cout * cin * 9, err);
+  const float* cb = cw ? t.get(p + std::to_string(conv_idx) + ".bias", cout, err) : nullptr;
+  BnFold bn;
+  if (!cb || !load_bn(t, p + std::to_string(conv_idx + 1), cout, &bn, err)) return 1;
+  std::vector<float> wf((size_t)cout * 9 * cin), bf(cout);
+  for (int co = 0; co < cout; ++co) {
+    for (int c = 0; c < cin; ++c)
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw)
+          wf[(size_t)co * 9 * cin + (kh * 3 + kw) * cin + c] = cw[(((size_t)co * cin + c) * 3 + kh) * 3 + kw] * bn.scale[co];
+    bf[co] = cb[co] * bn.scale[co] + bn.shift[co];
+  }
+  if (upload(w, to_bf16(wf), dw) || upload(w, bf, db)) return 1;
+  return 0;
+}
+
+int prep_dense_bf16(vfp_weights* w, const float* src, size_t n, __nv_bfloat16** dev) {
+  std::vector<float> v(src, src + n);
+  return upload(w, to_bf16(v), dev);
+}
+int prep_f32(vfp_weights* w, const float* src, size_t n, float** dev) {
+  std::vector<float> v(src, src + n);
+  return upload(w, v, dev);
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward workspace
+// ---------------------------------------------------------------------------------------------
+struct ForwardWs {
+  size_t cu, tok_pos, tok_len, c1, c2, c3, feat, xa, xb, xn, qkv, att, h, logits, xbf, pooled, total;
+};
+ForwardWs forward_ws_layout(int64_t F, int64_t C) {
+  ForwardWs L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  L.cu = take((size_t)(C + 1) * 4);
+  L.tok_pos = take((size_t)F * 4);
+  L.tok_len = take((size_t)F * 4);
+  L.c1 = take((size_t)F * 32 * 32 * 32 * 2);
+  L.c2 = take((size_t)F * 16 * 16 * 64 * 2);
+  L.c3 = take((size_t)F * 8 * 8 * 128 * 2);
+  L.feat = take((size_t)F * 256 * 2);
+  L.xa = take((size_t)F * kDim * 4);
+  L.xb = take((size_t)F * kDim * 4);
+  L.xn = take((size_t)F * kDim * 2);
+  L.qkv = take((size_t)F * 3 * kDim * 2);
+  L.att = take((size_t)F * kDim * 2);
+  L.h = take((size_t)F * 4 * kDim * 2);
+  L.logits = take((size_t)F * kDim * 4);
+  L.xbf = take((size_t)F * kDim * 2);
+  L.pooled = take((size_t)C * 3 * kDim * 4);
+  L.total = off;
+  return L;
+}
+
+constexpr int kMaxClipFrames = 1024;
+
+}  // namespace
+
+// =============================================================================================
+// exported functions
+// =============================================================================================
+extern "C" {
+
+int vfp_abi_version(void) { return VFP_ABI_VERSION; }
+const char* vfp_last_error(void) { return g_last_error.c_str(); }
+
+int vfp_device_sm_count(void) {
+  int n = 0, dev = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) return 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return sms;
+}
+
+unsigned int vfp_device_error_word(void) {
+  unsigned int v = 0, zero = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&v, g_vfp_device_error, sizeof(v));
+  if (v) cudaMemcpyToSymbol(g_vfp_device_error, &zero, sizeof(zero));
+  return v;
+}
+
+void vfp_weights_destroy(vfp_weights* w) {
+  if (!w) return;
+  for (void* p : w->allocs) cudaFree(p);
+  delete w;
+}
+
+int vfp_weights_embedding_dim(const vfp_weights* w) { return w ? w->embedding_dim : 0; }
+
+int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weights** out) {
+  if (!tensors || !out) return fail("vfp_weights_create: null argument");
+  if (vfp_device_sm_count() <= 0) return fail("vfp_weights_create: no CUDA device (there is no CPU fallback)");
+  if (!tensor_map_encoder()) return fail("vfp_weights_create: cuTensorMapEncodeTiled not available from the driver");
+  TensorTable t;
+  for (int i = 0; i < n_tensors; ++i) t.by_name[tensors[i].name] = &tensors[i];
+  std::string err;
+  vfp_weights* w = new vfp_weights();
+  auto bail = [&](const std::string& m) {
+    vfp_weights_destroy(w);
+    return fail("vfp_weights_create: " + (m.empty() ? g_last_error : m));
+  };
+  const std::string enc = "spatial_encoder.encoder.";
+
+  // ---- conv1 (3->32, k5): BN folded, packed as mma.sync B fragments [kh][n-tile][lane][2] ----
+  {
+    const float* cw = t.get(enc + "0.weight", 32 * 3 * 25, &err);
+    const float* cb = cw ? t.get(enc + "0.bias", 32, &err) : nullptr;
+    BnFold bn;
+    if (!cb || !load_bn(t, enc + "1", 32, &bn, &err)) return bail(err);
+    auto wk = [&](int co, int kh, int k) -> float {  // k = kw*3 + c, k == 15 is the zero pad
+      if (k >= 15) return 0.0f;
+      const int kw = k / 3, c = k % 3;
+      return cw[((co * 3 + c) * 5 + kh) * 5 + kw] * bn.scale[co];
+    };
+    std::vector<uint32_t> pack(5 * 4 * 32 * 2);
+    for (int kh = 0; kh < 5; ++kh)
+      for (int nt = 0; nt < 4; ++nt)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int g = lane >> 2, tig = lane & 3, co = nt * 8 + g;
+          for (int r = 0; r < 2; ++r) {
+            const int k0 = 2 * tig + 8 * r;
+            const __nv_bfloat16 lo = __float2bfloat16(wk(co, kh, k0)), hi = __float2bfloat16(wk(co, kh, k0 + 1));
+            uint16_t l16, h16;
+            memcpy(&l16, &lo, 2);
+            memcpy(&h16, &hi, 2);
+            pack[((kh * 4 + nt) * 32 + lane) * 2 + r] = (uint32_t)l16 | ((uint32_t)h16 << 16);
+          }
+        }
+    std::vector<float> bias(32);
+    for (int co = 0; co < 32; ++co) bias[co] = cb[co] * bn.scale[co] + bn.shift[co];
+    if (upload(w, pack, &w->c1_wpack) || upload(w, bias, &w->c1_bias)) return bail("");
+  }
+  // ---- conv2..4 ----
+  if (prep_conv3x3(w, t, 3, 32, 64, &w->c2_w, &w->c2_b, &err)) return bail(err);
+  if (prep_conv3x3(w, t, 6, 64, 128, &w->c3_w, &w->c3_b, &err)) return bail(err);
+  if (prep_conv3x3(w, t, 9, 128, 256, &w->c4_w, &w->c4_b, &err)) return bail(err);
+
+  // ---- Linear(256->S) o Linear(S->256) folded, + positional table ----
+  {
+    const int64_t s_numel = t.numel(enc + "14.bias");
+    if (s_numel <= 0) return bail("missing checkpoint tensor: " + enc + "14.bias");
+    const int S = (int)s_numel;
+    const float* ws = t.get(enc + "14.weight", (int64_t)S * 256, &err);
+    const float* bs = ws ? t.get(enc + "14.bias", S, &err) : nullptr;
+    const float* wt = bs ? t.get("temporal_projection.weight", (int64_t)kDim * S, &err) : nullptr;
+    const float* bt = wt ? t.get("temporal_projection.bias", kDim, &err) : nullptr;
+    if (!bt) return bail(err.empty() ? "temporal_dim must be 256" : err);
+    std::vector<float> wf((size_t)kDim * 256), bf(kDim);
+    for (int o = 0; o < kDim; ++o) {
+      for (int i = 0; i < 256; ++i) {
+        double acc = 0;
+        for (int s = 0; s < S; ++s) acc += (double)wt[(size_t)o * S + s] * (double)ws[(size_t)s * 256 + i];
+        wf[(size_t)o * 256 + i] = (float)acc;
+      }
+      double acc = bt[o];
+      for (int s = 0; s < S; ++s) acc += (double)wt[(size_t)o * S + s] * (double)bs[s];
+      bf[o] = (float)acc;
+    }
+    if (upload(w, to_bf16(wf), &w->wtok) || upload(w, bf, &w->btok)) return bail("");
+    const int64_t pe_numel = t.numel("pos_encoding.pe");
+    if (pe_numel <= 0 || pe_numel % kDim) return bail("missing or malformed checkpoint tensor: pos_encoding.pe");
+    w->pe_len = (int)(pe_numel / kDim);
+    if (prep_f32(w, t.get("pos_encoding.pe", pe_numel, &err), (size_t)pe_numel, &w->pe)) return bail("");
+  }
+  // ---- temporal conv blocks: BN folded, 11 centred taps, layout [ci][tap][o] ----
+  for (int blk = 0; blk < 2; ++blk) {
+    std::vector<float> wf(4 * 11 * kDim, 0.0f), bf(kDim);
+    for (int j = 0; j < 4; ++j) {
+      const int k = kTemporalKernels[j], off = (11 - k) / 2;
+      const std::string p = "temporal_conv_blocks." + std::to_string(blk) + ".convs." + std::to_string(j);
+      const float* cw = t.get(p + ".0.weight", 64 * 4 * k, &err);
+      const float* cb = cw ? t.get(p + ".0.bias", 64, &err) : nullptr;
+      BnFold bn;
+      if (!cb || !load_bn(t, p + ".1", 64, &bn, &err)) return bail(err);
+      for (int g = 0; g < 64; ++g) {
+        const int o = j * 64 + g;
+        for (int ci = 0; ci < 4; ++ci)
+          for (int dt = 0; dt < k; ++dt) wf[(ci * 11 + off + dt) * kDim + o] = cw[(g * 4 + ci) * k + dt] * bn.scale[g];
+        bf[o] = cb[g] * bn.scale[g] + bn.shift[g];
+      }
+    }
+    if (upload(w, wf, &w->tc_w[blk]) || upload(w, bf, &w->tc_b[blk])) return bail("");
+  }
+  // ---- attention blocks ----
+  while (t.has("attention_blocks." + std::to_string(w->n_attn) + ".norm1.weight")) ++w->n_attn;
+  w->attn.resize(w->n_attn);
+  for (int b = 0; b < w->n_attn; ++b) {
+    const std::string p = "attention_blocks." + std::to_string(b);
+    AttnBlockWeights& a = w->attn[b];
+    struct F32Item { const char* key; int64_t n; float** dst; };
+    const F32Item f32s[] = {
+        {".norm1.weight", kDim, &a.ln1_w}, {".norm1.bias", kDim, &a.ln1_b}, {".norm2.weight", kDim, &a.ln2_w},
+        {".norm2.bias", kDim, &a.ln2_b},   {".attn.in_proj_bias", 3 * kDim, &a.bqkv},
+        {".attn.out_proj.bias", kDim, &a.bo}, {".conv1.bias", 4 * kDim, &a.b1}, {".conv2.bias", kDim, &a.b2}};
+    for (const F32Item& it : f32s) {
+      const float* src = t.get(p + it.key, it.n, &err);
+      if (!src) return bail(err);
+      if (prep_f32(w, src, (size_t)it.n, it.dst)) return bail("");
+    }
+    struct BfItem { const char* key; int64_t n; __nv_bfloat16** dst; };
+    const BfItem bfs[] = {{".attn.in_proj_weight", 3 * kDim * kDim, &a.wqkv}, {".attn.out_proj.weight", kDim * kDim, &a.wo},
+                          {".conv1.weight", 4 * kDim * kDim, &a.w1},          {".conv2.weight", 4 * kDim * kDim, &a.w2}};
+    for (const BfItem& it : bfs) {
+      const float* src = t.get(p + it.key, it.n, &err);
+      if (!src) return bail(err);
+      if (prep_dense_bf16(w, src, (size_t)it.n, it.dst)) return bail("");
+    }
+    if (make_tmap_rows_bf16(&a.tm_qkv, a.wqkv, 3 * kDim, kDim, kDim, 256, 64) ||
+        make_tmap_rows_bf16(&a.tm_o, a.wo, kDim, kDim, kDim, 256, 64) ||
+        make_tmap_rows_bf16(&a.tm_w1, a.w1, 4 * kDim, kDim, kDim, 256, 64) ||
+        make_tmap_rows_bf16(&a.tm_w2, a.w2, kDim, 4 * kDim, 4 * kDim, 256, 64))
+      return bail("tensor map encode failed (attention weights)");
+  }
+  // ---- pooling + head ----
+  {
+    const float* wp = t.get("temporal_pool.0.weight", kDim * kDim, &err);
+    const float* bp = wp ? t.get("temporal_pool.0.bias", kDim, &err) : nullptr;
+    const float* w0 = bp ? t.get("final_projection.0.weight", (int64_t)kDim * 3 * kDim, &err) : nullptr;
+    const float* b0 = w0 ? t.get("final_projection.0.bias", kDim, &err) : nullptr;
+    if (!b0) return bail(err);
+    const int64_t d_numel = t.numel("final_projection.3.bias");
+    if (d_numel <= 0 || d_numel > 512) return bail("final_projection.3.bias missing or embedding_dim > 512");
+    const int D = (int)d_numel;
+    const float* w3 = t.get("final_projection.3.weight", (int64_t)D * kDim, &err);
+    const float* b3 = w3 ? t.get("final_projection.3.bias", D, &err) : nullptr;
+    if (!b3) return bail(err);
+    w->embedding_dim = D;
+    std::vector<float> w0t((size_t)3 * kDim * kDim), w3t((size_t)kDim * D);
+    for (int o = 0; o < kDim; ++o)
+      for (int k = 0; k < 3 * kDim; ++k) w0t[(size_t)k * kDim + o] = w0[(size_t)o * 3 * kDim + k];
+    for (int o = 0; o < D; ++o)
+      for (int k = 0; k < kDim; ++k) w3t[(size_t)k * D + o] = w3[(size_t)o * kDim + k];
+    if (prep_dense_bf16(w, wp, (size_t)kDim * kDim, &w->wpool) || prep_f32(w, bp, kDim, &w->bpool) ||
+        upload(w, w0t, &w->w0t) || prep_f32(w, b0, kDim, &w->b0) || upload(w, w3t, &w->w3t) ||
+        prep_f32(w, b3, (size_t)D, &w->b3))
+      return bail("");
+  }
+  if (make_tmap_rows_bf16(&w->tm_c2, w->c2_w, 64, 288, 288, 64, 32) ||
+      make_tmap_rows_bf16(&w->tm_c3, w->c3_w, 128, 576, 576, 128, 64) ||
+      make_tmap_rows_bf16(&w->tm_c4, w->c4_w, 256, 1152, 1152, 256, 64) ||
+      make_tmap_rows_bf16(&w->tm_tok, w->wtok, kDim, 256, 256, 256, 64) ||
+      make_tmap_rows_bf16(&w->tm_pool, w->wpool, kDim, kDim, kDim, 256, 64))
+    return bail("tensor map encode failed (weights)");
+  VFP_CUDA(cudaDeviceSynchronize());
+  *out = w;
+  return 0;
+}
+
+size_t vfp_forward_workspace_bytes(int64_t frames_per_pass, int64_t clips_per_pass) {
+  if (frames_per_pass <= 0) return 0;
+  if (clips_per_pass <= 0 || clips_per_pass > frames_per_pass) clips_per_pass = frames_per_pass;
+  return forward_ws_layout(frames_per_pass, clips_per_pass).total;
+}
+
+}  // extern "C"
+
+namespace {
+
+// One pass: clips [c0, c1) = frames [f0, f0 + F) of the packed input.
+int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dtype, size_t frame_bytes,
+                 const int32_t* cu_host, int c0, int c1, float* emb_out, float* features_out, uint8_t* ws,
+                 cudaStream_t st) {
+  const int C = c1 - c0;
+  const int64_t f0 = cu_host[c0];
+  const int64_t F = cu_host[c1] - f0;
+  const ForwardWs L = forward_ws_layout(F, C);
+  int* d_cu = reinterpret_cast<int*>(ws + L.cu);
+  int* tok_pos = reinterpret_cast<int*>(ws + L.tok_pos);
+  int* tok_len = reinterpret_cast<int*>(ws + L.tok_len);
+  __nv_bfloat16* c1a = reinterpret_cast<__nv_bfloat16*>(ws + L.c1);
+  __nv_bfloat16* c2a = reinterpret_cast<__nv_bfloat16*>(ws + L.c2);
+  __nv_bfloat16* c3a = reinterpret_cast<__nv_bfloat16*>(ws + L.c3);
+  __nv_bfloat16* feat = reinterpret_cast<__nv_bfloat16*>(ws + L.feat);
+  float* xa = reinterpret_cast<float*>(ws + L.xa);
+  float* xb = reinterpret_cast<float*>(ws + L.xb);
+  __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(ws + L.xn);
+  __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws + L.qkv);
+  __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws + L.att);
+  __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(ws + L.h);
+  float* logits = reinterpret_cast<float*>(ws + L.logits);
+  __nv_bfloat16* xbf = reinterpret_cast<__nv_bfloat16*>(ws + L.xbf);
+  float* pooled = reinterpret_cast<float*>(ws + L.pooled);
+
+  // clip prefix sums relative to this pass
+  std::vector<int32_t> cu_rel(C + 1);
+  int max_T = 0;
+  for (int i = 0; i <= C; ++i) cu_rel[i] = (int32_t)(cu_host[c0 + i] - f0);
+  for (int i = 0; i < C; ++i) max_T = std::max(max_T, cu_rel[i + 1] - cu_rel[i]);
+  VFP_CUDA(cudaMemcpyAsync(d_cu, cu_rel.data(), (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, st));
+  // cu_rel is pageable: the copy is staged before the call returns, so the vector may die with this scope.
+  token_map_kernel<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(d_cu, C, (int)F, tok_pos, tok_len);
+
+  // ---- frame encoder ----
+  const int sms = device_sm_count();
+  {
+    const long long grid = std::min<long long>(F, (long long)sms * 8);
+    conv1_stem_kernel<<<(unsigned)grid, kC1Threads, 0, st>>>(frames_base + (size_t)f0 * frame_bytes, frame_dtype, F,
+                                                            w->c1_wpack, w->c1_bias, c1a);
+  }
+  CUtensorMap ta;
+  {  // conv2: 32x32x32 -> 16x16x64, tile = 8 output rows x 16 cols of one frame
+    if (make_tmap_conv_s2_bf16(&ta, c1a, F, 32, 32, 32, 32, 16, 8, 1)) return fail("tensor map encode failed (conv2)");
+    GemmShape s{};
+    s.m_tiles = (int)(2 * F); s.n_tiles = 1; s.k_blocks = 9; s.group_m = 16; s.a_conv = 1;
+    s.tiles_per_frame = 2; s.frames_per_tile = 1; s.tile_out_rows = 8; s.cblocks_per_tap = 1;
+    EpiBiasAct::Params ep{};
+    ep.bias = w->c2_b; ep.out_bf16 = c2a; ep.ld_out = 64; ep.M = (int)(F * 256); ep.N = 64; ep.act = 1;
+    VFP_CUDA((launch_gemm<64, 32, 8, EpiBiasAct>(ta, w->tm_c2, s, ep, st)));
+  }
+  {  // conv3: 16x16x64 -> 8x8x128, tile = 2 frames
+    if (make_tmap_conv_s2_bf16(&ta, c2a, F, 16, 16, 64, 64, 8, 8, 2)) return fail("tensor map encode failed (conv3)");
+    GemmShape s{};
+    s.m_tiles = (int)((F + 1) / 2); s.n_tiles = 1; s.k_blocks = 9; s.group_m = 16; s.a_conv = 1;
+    s.tiles_per_frame = 1; s.frames_per_tile = 2; s.tile_out_rows = 8; s.cblocks_per_tap = 1;
+    EpiBiasAct::Params ep{};
+    ep.bias = w->c3_b; ep.out_bf16 = c3a; ep.ld_out = 128; ep.M = (int)(F * 64); ep.N = 128; ep.act = 1;
+    VFP_CUDA((launch_gemm<128, 64, 6, EpiBiasAct>(ta, w->tm_c3, s, ep, st)));
+  }
+  {  // conv4: 8x8x128 -> 4x4x256 + ReLU + global average pool, tile = 8 frames
+    if (make_tmap_conv_s2_bf16(&ta, c3a, F, 8, 8, 128, 64, 4, 4, 8)) return fail("tensor map encode failed (conv4)");
+    GemmShape s{};
+    s.m_tiles = (int)((F + 7) / 8); s.n_tiles = 1; s.k_blocks = 18; s.group_m = 16; s.a_conv = 1;
+    s.tiles_per_frame = 1; s.frames_per_tile = 8; s.tile_out_rows = 4; s.cblocks_per_tap = 2;
+    EpiConvPool16::Params ep{};
+    ep.bias = w->c4_b; ep.out_bf16 = feat; ep.frames = (int)F; ep.N = 256;
+    VFP_CUDA((launch_gemm<256, 64, 4, EpiConvPool16>(ta, w->tm_c4, s, ep, st)));
+  }
+  // ---- token embedding: x = Wtok feat + btok + pe[pos] ----
+  auto token_gemm = [&](const __nv_bfloat16* A, int K, const CUtensorMap& tb, int N, const EpiBiasAct::Params& ep) -> int {
+    CUtensorMap tma;
+    if (make_tmap_rows_bf16(&tma, A, (uint64_t)F, (uint64_t)K, (uint64_t)K, 128, 64)) return fail("tensor map encode failed (tokens)");
+    GemmShape s = plain_shape(F, N, K, 256, 64, 32);
+    VFP_CUDA((launch_gemm<256, 64, 4, EpiBiasAct>(tma, tb, s, ep, st)));
+    return 0;
+  };
+  {
+    EpiBiasAct::Params ep{};
+    ep.bias = w->btok; ep.pe = w->pe; ep.token_pos = tok_pos; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
+    if (token_gemm(feat, 256, w->tm_tok, kDim, ep)) return 1;
+  }
+  // ---- multi-scale temporal convolutions (residual) ----
+  {
+    const unsigned grid = (unsigned)((F + 7) / 8);
+    temporal_conv_kernel<<<grid, 256, 0, st>>>(xa, tok_pos, tok_len, w->tc_w[0], w->tc_b[0], xb, (int)F);
+    temporal_conv_kernel<<<grid, 256, 0, st>>>(xb, tok_pos, tok_len, w->tc_w[1], w->tc_b[1], xa, (int)F);
+  }
+  // ---- attention blocks ----
+  const unsigned ln_grid = (unsigned)((F * 32 + 255) / 256);
+  const size_t att_smem = (size_t)max_T * 128;
+  static bool att_configured = false;
+  if (!att_configured) {
+    VFP_CUDA(cudaFuncSetAttribute(attention_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxClipFrames * 128));
+    att_configured = true;
+  }
+  for (int b = 0; b < w->n_attn; ++b) {
+    const AttnBlockWeights& a = w->attn[b];
+    layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, a.ln1_w, a.ln1_b, xn, (int)F);
+    {
+      EpiBiasAct::Params ep{};
+      ep.bias = a.bqkv; ep.out_bf16 = qkv; ep.ld_out = 3 * kDim; ep.M = (int)F; ep.N = 3 * kDim;
+      if (token_gemm(xn, kDim, a.tm_qkv, 3 * kDim, ep)) return 1;
+    }
+    attention_clip_kernel<<<dim3((unsigned)C, kHeads), 128, att_smem, st>>>(qkv, d_cu, att);
+    {
+      EpiBiasAct::Params ep{};
+      ep.bias = a.bo; ep.residual = xa; ep.ld_res = kDim; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
+      if (token_gemm(att, kDim, a.tm_o, kDim, ep)) return 1;
+    }
+    layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, a.ln2_w, a.ln2_b, xn, (int)F);
+    {
+      EpiBiasAct::Params ep{};
+      ep.bias = a.b1; ep.act = 2; ep.out_bf16 = hbuf; ep.ld_out = 4 * kDim; ep.M = (int)F; ep.N = 4 * kDim;
+      if (token_gemm(xn, kDim, a.tm_w1, 4 * kDim, ep)) return 1;
+    }
+    {
+      EpiBiasAct::Params ep{};
+      ep.bias = a.b2; ep.residual = xa; ep.ld_res = kDim; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
+      if (token_gemm(hbuf, 4 * kDim, a.tm_w2, kDim, ep)) return 1;
+    }
+  }
+  if (features_out)
+    VFP_CUDA(cudaMemcpyAsync(features_out + (size_t)f0 * kDim, xa, (size_t)F * kDim * 4, cudaMemcpyDeviceToDevice, st));
+  // ---- pooling + head ----
+  f32_to_bf16_kernel<<<(unsigned)((F * kDim / 8 + 255) / 256), 256, 0, st>>>(xa, xbf, F * kDim / 8);
+  {
+    EpiBiasAct::Params ep{};
+    ep.bias = w->bpool; ep.act = 1; ep.out_f32 = logits; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
+    if (token_gemm(xbf, kDim, w->tm_pool, kDim, ep)) return 1;
+  }
+  temporal_pool_kernel<<<(unsigned)C, 256, 0, st>>>(xa, logits, d_cu, pooled);
+  final_projection_kernel<8><<<(unsigned)((C + 7) / 8), 256, 0, st>>>(pooled, w->w0t, w->b0, w->w3t, w->b3, w->embedding_dim,
+                                                                   C, emb_out + (size_t)c0 * w->embedding_dim);
+  VFP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vfp_forward(const vfp_weights* w, const void* frames, int frame_dtype, const int32_t* cu, int n_clips,
+                float* emb_out, float* features_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!w || !frames || !cu || !emb_out || !workspace) return fail("vfp_forward: null argument");
+  if (n_clips <= 0) return fail("vfp_forward: n_clips must be positive");
+  if (frame_dtype < 0 || frame_dtype > 2) return fail("vfp_forward: unknown frame dtype");
+  const size_t frame_bytes = (size_t)12288 * (frame_dtype == VFP_FRAME_U8 ? 1 : frame_dtype == VFP_FRAME_BF16 ? 2 : 4);
+  if (cu[0] != 0) return fail("vfp_forward: cu_seqlens[0] must be 0");
+  int max_T = 0;
+  for (int i = 0; i < n_clips; ++i) {
+    const int T = cu[i + 1] - cu[i];
+    if (T <= 0) return fail("vfp_forward: clip " + std::to_string(i) + " has no frames");
+    if (T > kMaxClipFrames || T > w->pe_len)
+      return fail("vfp_forward: clip " + std::to_string(i) + " has " + std::to_string(T) + " frames; limit is " +
+                  std::to_string(std::min(kMaxClipFrames, w->pe_len)));
+    max_T = std::max(max_T, T);
+  }
+  // largest pass (in frames) the workspace can hold; a pass never has more clips than frames
+  int64_t lo = 0, hi = cu[n_clips];
+  while (lo < hi) {
+    const int64_t mid = (lo + hi + 1) / 2;
+    if (forward_ws_layout(mid, std::min<int64_t>(mid, n_clips)).total <= workspace_bytes) lo = mid; else hi = mid - 1;
+  }
+  const int64_t pass_frames = lo;
+  if (pass_frames < max_T)
+    return fail("vfp_forward: workspace of " + std::to_string(workspace_bytes) + " bytes cannot hold the longest clip (" +
+                std::to_string(max_T) + " frames need " + std::to_string(forward_ws_layout(max_T, 1).total) + ")");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int c0 = 0;
+  while (c0 < n_clips) {
+    int c1 = c0;
+    while (c1 < n_clips && (int64_t)cu[c1 + 1] - cu[c0] <= pass_frames) ++c1;
+    if (int rc = forward_pass(w, static_cast<const uint8_t*>(frames), frame_dtype, frame_bytes, cu, c0, c1, emb_out,
+                              features_out, static_cast<uint8_t*>(workspace), st))
+      return rc;
+    c0 = c1;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// similarity join
+// ---------------------------------------------------------------------------------------------
+size_t vfp_join_workspace_bytes(int64_t n_q, int64_t n_db, int64_t candidate_capacity) {
+  if (n_q <= 0 || n_db <= 0) return 0;
+  if (candidate_capacity < 1024) candidate_capacity = 1024;
+  return align_up((size_t)n_q * 512, 1024) + align_up((size_t)n_db * 512, 1024) +
+         3 * align_up((size_t)candidate_capacity * 4, 1024) + 1024;
+}
+
+int vfp_join_threshold(const float* q, const float* db, int64_t n_q, int64_t n_db, int dim, int64_t q_row0, float thr,
+                       float screen_margin, int32_t* out_i, int32_t* out_j, float* out_s, int64_t capacity,
+                       uint64_t* counts_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!q || !db || !out_i || !out_j || !out_s || !counts_out || !workspace) return fail("vfp_join_threshold: null argument");
+  if (dim != 256) return fail("vfp_join_threshold: dim must be 256");
+  if (n_q <= 0 || n_db <= 0) return fail("vfp_join_threshold: empty operand");
+  if (n_q > 0x7fffff00LL || n_db > 0x7fffff00LL || q_row0 + n_q > 0x7fffff00LL) return fail("vfp_join_threshold: more than 2^31 rows");
+  if (!(screen_margin >= 0.0f)) return fail("vfp_join_threshold: screen_margin must be >= 0");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  const bool self_join = (q == db && n_q == n_db);
+  const size_t q_bytes = align_up((size_t)n_q * 512, 1024), db_bytes = align_up((size_t)n_db * 512, 1024);
+  const size_t fixed = q_bytes + db_bytes + 1024;
+  if (workspace_bytes < fixed + 3 * 4096) return fail("vfp_join_threshold: workspace too small; see vfp_join_workspace_bytes");
+  const int64_t cand_cap = (int64_t)((workspace_bytes - fixed) / 3 / 1024 * 1024 / 4);
+  __nv_bfloat16* qbf = reinterpret_cast<__nv_bfloat16*>(ws);
+  __nv_bfloat16* dbbf = self_join ? qbf : reinterpret_cast<__nv_bfloat16*>(ws + q_bytes);
+  int* cand_i = reinterpret_cast<int*>(ws + q_bytes + db_bytes);
+  int* cand_j = cand_i + cand_cap;
+  float* cand_s = reinterpret_cast<float*>(cand_j + cand_cap);
+  unsigned long long* cand_count = reinterpret_cast<unsigned long long*>(ws + q_bytes + db_bytes + 3 * (size_t)cand_cap * 4);
+  unsigned long long* counts = reinterpret_cast<unsigned long long*>(counts_out);
+
+  VFP_CUDA(cudaMemsetAsync(cand_count, 0, 8, st));
+  VFP_CUDA(cudaMemsetAsync(counts, 0, 16, st));
+  f32_to_bf16_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, st>>>(q, qbf, n_q * 32);
+  if (!self_join) f32_to_bf16_kernel<<<(unsigned)((n_db * 32 + 255) / 256), 256, 0, st>>>(db, dbbf, n_db * 32);
+  CUtensorMap ta, tb;
+  if (make_tmap_rows_bf16(&ta, qbf, (uint64_t)n_q, 256, 256, 128, 64) ||
+      make_tmap_rows_bf16(&tb, dbbf, (uint64_t)n_db, 256, 256, 256, 64))
+    return fail("vfp_join_threshold: tensor map encode failed");
+  GemmShape s = plain_shape(n_q, 0, 256, 256, 64, 32);
+  s.n_tiles = (int)((n_db + 255) / 256);
+  EpiJoinThreshold::Params ep{};
+  ep.thr = thr - screen_margin;
+  ep.q_rows = n_q; ep.db_rows = n_db; ep.q_row0 = q_row0;
+  ep.out_i = cand_i; ep.out_j = cand_j; ep.out_s = cand_s; ep.count = cand_count; ep.capacity = cand_cap;
+  VFP_CUDA((launch_gemm<256, 64, 4, EpiJoinThreshold>(ta, tb, s, ep, st)));
+  rescore_pairs_kernel<<<device_sm_count() * 4, 256, 0, st>>>(q, db, dim, q_row0, cand_i, cand_j, cand_count, cand_cap, thr,
+                                                              out_i, out_j, out_s, counts, capacity);
+  // counts[1] = candidate count (device-side copy so the caller reads both with one transfer)
+  VFP_CUDA(cudaMemcpyAsync(counts + 1, cand_count, 8, cudaMemcpyDeviceToDevice, st));
+  VFP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// flat inner-product top-k
+// ---------------------------------------------------------------------------------------------
+size_t vfp_topk_workspace_bytes(int64_t n_q, int64_t n_db, int k) { return topk_workspace_bytes(n_q, n_db, k); }
+
+int vfp_topk_ip(const float* q, const float* db, int64_t n_q, int64_t n_db, int dim, int k, float screen_margin,
+                float* out_s, int64_t* out_idx, uint64_t* flags_out, void* workspace, size_t workspace_bytes,
+                void* stream) {
+  if (!q || !db || !out_s || !out_idx || !flags_out || !workspace) return fail("vfp_topk_ip: null argument");
+  if (dim != 256) return fail("vfp_topk_ip: dim must be 256");
+  if (k <= 0 || k > 32) return fail("vfp_topk_ip: k must be in [1, 32]");
+  if (n_q <= 0 || n_db <= 0) return fail("vfp_topk_ip: empty operand");
+  if (n_db < k) return fail("vfp_topk_ip: k exceeds the number of database rows");
+  if (n_q > 0x7fffff00LL || n_db > 0x7fffff00LL) return fail("vfp_topk_ip: more than 2^31 rows");
+  if (workspace_bytes < topk_workspace_bytes(n_q, n_db, k)) return fail("vfp_topk_ip: workspace too small; see vfp_topk_workspace_bytes");
+  std::string err;
+  const int rc = topk_run(q, db, n_q, n_db, k, screen_margin, out_s, out_idx, reinterpret_cast<unsigned long long*>(flags_out),
+                          static_cast<uint8_t*>(workspace), static_cast<cudaStream_t>(stream), &err);
+  if (rc) return fail("vfp_topk_ip: " + err);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+"""Drop-in for the reference model factory (/root/reference/model.py:585-610) and attention model
+(/root/reference/model.py:182-298), inference only.
+
+`create_model("attention", ...)` returns an ``nn.Module`` whose ``state_dict()`` has the reference's 144 keys,
+shapes and dtypes (so ``load_state_dict(checkpoint["model_state_dict"])`` from fingerprint.py:70 works
+unchanged, and default construction under a fixed ``torch.manual_seed`` yields the reference's initial
+weights), but whose ``forward`` does not run any PyTorch operator: it hands raw device pointers to
+``vfp_forward`` in libvfp_b200.so (hand-written sm_100a kernels). The parameter-holding submodules exist only
+to own tensors under the right names.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _native
+
+_TEMPORAL_KERNELS = (3, 5, 7, 11)
+_NUM_HEADS = 8
+
+
+class _ParamsOnly(nn.Module):
+    """Base for containers that own parameters but are never called."""
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container: compute happens in libvfp_b200.so, not in PyTorch modules")
+
+
+class PositionalEncoding(_ParamsOnly):
+    """Owns the persistent sinusoidal buffer `pe` (1, max_len, d) of model.py:74-89."""
+
+    def __init__(self, d_model: int, max_len: int = 10000):
+        super().__init__()
+        angle = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1) * torch.exp(
+            torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model)
+        )
+        table = torch.zeros(max_len, d_model)
+        table[:, 0::2] = torch.sin(angle)
+        table[:, 1::2] = torch.cos(angle)
+        self.register_buffer("pe", table.unsqueeze(0))
+
+
+class SpatialEncoder(_ParamsOnly):
+    """Parameter layout of model.py:92-121: `encoder.{0,3,6,9}` convs, `{1,4,7,10}` batch norms, `14` linear."""
+
+    STAGES = ((3, 32, 5, 2), (32, 64, 3, 1), (64, 128, 3, 1), (128, 256, 3, 1))  # cin, cout, kernel, padding
+
+    def __init__(self, in_channels: int = 3, out_dim: int = 128):
+        super().__init__()
+        layers: List[nn.Module] = []
+        for cin, cout, k, pad in self.STAGES:
+            layers += [nn.Conv2d(in_channels if cin == 3 else cin, cout, k, stride=2, padding=pad), nn.BatchNorm2d(cout), nn.ReLU(inplace=True)]
+        layers += [nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(256, out_dim)]
+        self.encoder = nn.Sequential(*layers)
+
+
+class TemporalConvBlock(_ParamsOnly):
+    """model.py:155-179: `convs.{j}.0` grouped Conv1d(dim -> dim/n, k_j, groups=dim/n), `convs.{j}.1` BatchNorm1d."""
+
+    def __init__(self, dim: int, kernel_sizes: Sequence[int] = _TEMPORAL_KERNELS):
+        super().__init__()
+        width = dim // len(kernel_sizes)
+        self.convs = nn.ModuleList(
+            nn.Sequential(nn.Conv1d(dim, width, k, padding=k // 2, groups=width), nn.BatchNorm1d(width), nn.ReLU(inplace=True))
+            for k in kernel_sizes
+        )
+
+
+class TemporalAttentionBlock(_ParamsOnly):
+    """model.py:124-152: norm1, attn (packed in_proj + out_proj), norm2, conv1 (1x1, dim->4dim), conv2 (1x1)."""
+
+    def __init__(self, dim: int, num_heads: int = _NUM_HEADS, mlp_ratio: int = 4, drop: float = 0.1):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = nn.MultiheadAttention(dim, num_heads, dropout=drop, batch_first=True)
+        self.norm2 = nn.LayerNorm(dim)
+        self.conv1 = nn.Conv1d(dim, dim * mlp_ratio, 1)
+        self.act = nn.GELU()
+        self.conv2 = nn.Conv1d(dim * mlp_ratio, dim, 1)
+        self.drop = nn.Dropout(drop)
+
+
+class VideoFingerprintAttention(nn.Module):
+    """Fingerprint model: (B,T,3,64,64) frames in [0,1] -> unit-norm (B, embedding_dim) embeddings."""
+
+    def __init__(self, spatial_dim=128, temporal_dim=256, embedding_dim=256, num_attention_blocks=4, num_heads=_NUM_HEADS):
+        super().__init__()
+        if temporal_dim != 256 or num_heads != 8:
+            raise ValueError("the sm_100a kernels are specialised for temporal_dim=256 with 8 heads (reference defaults)")
+        self.spatial_encoder = SpatialEncoder(out_dim=spatial_dim)
+        self.temporal_projection = nn.Linear(spatial_dim, temporal_dim)
+        self.pos_encoding = PositionalEncoding(temporal_dim)
+        self.temporal_conv_blocks = nn.ModuleList(TemporalConvBlock(temporal_dim) for _ in range(2))
+        self.attention_blocks = nn.ModuleList(TemporalAttentionBlock(temporal_dim, num_heads) for _ in range(num_attention_blocks))
+        self.temporal_pool = nn.Sequential(nn.Conv1d(temporal_dim, temporal_dim, 1), nn.ReLU(inplace=True))
+        self.final_projection = nn.Sequential(
+            nn.Linear(temporal_dim * 3, temporal_dim), nn.ReLU(inplace=True), nn.Dropout(0.1), nn.Linear(temporal_dim, embedding_dim)
+        )
+        self.temperature = nn.Parameter(torch.ones(1) * 0.07)
+        self.embedding_dim = embedding_dim
+        self.frames_per_pass = 8192  # frames pushed through the network per internal pass (workspace ~ 124 KB/frame)
+        self._native_weights: Optional[int] = None
+        self._native_key: Optional[tuple] = None
+        self._workspace: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ native weight handle
+    def _weights_key(self) -> tuple:
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def _release_native(self) -> None:
+        if self._native_weights is not None:
+            try:
+                _native.load().vfp_weights_destroy(C.c_void_p(self._native_weights))
+            except Exception:  # pragma: no cover - interpreter teardown
+                pass
+            self._native_weights = None
+            self._native_key = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self._release_native()
+        except Exception:  # interpreter teardown: torch internals may already be gone
+            pass
+
+    def _ensure_native(self) -> int:
+        """(Re)build the folded / packed device weights whenever a parameter or buffer changed."""
+        key = self._weights_key()
+        if self._native_weights is not None and key == self._native_key:
+            return self._native_weights
+        self._release_native()
+        lib = _native.load()
+        host = {k: v.detach().to("cpu").contiguous() for k, v in self.state_dict().items()}
+        host = {k: (v.float() if v.is_floating_point() else v) for k, v in host.items()}
+        descs = (_native.TensorDesc * len(host))()
+        for i, (k, v) in enumerate(host.items()):
+            descs[i] = _native.TensorDesc(k.encode(), v.data_ptr(), v.numel())
+        handle = C.c_void_p()
+        _native.check(lib.vfp_weights_create(descs, len(host), C.byref(handle)), "vfp_weights_create")
+        self._native_weights = handle.value
+        self._native_key = key
+        return self._native_weights
+
+    def _get_workspace(self, nbytes: int, device) -> torch.Tensor:
+        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != device:
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return self._workspace
+
+    # ------------------------------------------------------------------ packed (variable-length) entry
+    @torch.no_grad()
+    def fingerprint_packed(self, frames: torch.Tensor, lengths: Sequence[int], return_features: bool = False):
+        """frames: (sum T, 3, 64, 64) uint8 / bf16 / fp32 on the GPU, clips back to back; lengths: frames per clip.
+        Every clip gets exactly the embedding a B=1 reference forward on that clip alone would give."""
+        _native.require_cuda()
+        if self.training:
+            raise RuntimeError("inference only: call .eval() first (the reference scanner does, fingerprint.py:33)")
+        lengths = [int(t) for t in lengths]
+        total = sum(lengths)
+        if frames.dim() != 4 or tuple(frames.shape[1:]) != (3, 64, 64) or frames.shape[0] != total:
+            raise ValueError(f"frames must be (sum(lengths)={total}, 3, 64, 64), got {tuple(frames.shape)}")
+        if not frames.is_cuda:
+            frames = frames.cuda()
+        if frames.dtype == torch.uint8:
+            code = _native.FRAME_U8
+        elif frames.dtype == torch.bfloat16:
+            code = _native.FRAME_BF16
+        else:
+            code = _native.FRAME_F32
+            frames = frames.float()
+        frames = frames.contiguous()
+        dev = frames.device
+        lib = _native.load()
+        with torch.cuda.device(dev):
+            weights = self._ensure_native()
+            n = len(lengths)
+            cu = (C.c_int32 * (n + 1))()
+            acc = 0
+            for i, t in enumerate(lengths):
+                cu[i] = acc
+                acc += t
+            cu[n] = acc
+            pass_frames = max(min(total, self.frames_per_pass), max(lengths))
+            ws = self._get_workspace(lib.vfp_forward_workspace_bytes(pass_frames, min(pass_frames, n)), dev)
+            emb = torch.empty((n, self.embedding_dim), dtype=torch.float32, device=dev)
+            feats = torch.empty((total, 256), dtype=torch.float32, device=dev) if return_features else None
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = lib.vfp_forward(
+                C.c_void_p(weights), C.c_void_p(frames.data_ptr()), code, C.cast(cu, C.c_void_p), n,
+                C.c_void_p(emb.data_ptr()), C.c_void_p(feats.data_ptr() if feats is not None else None),
+                C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(stream),
+            )
+            _native.check(rc, "vfp_forward")
+        return (emb, feats) if return_features else emb
+
+    def fingerprint_clips(self, clips: Sequence[torch.Tensor]) -> torch.Tensor:
+        """List of (T_i,3,64,64) clips -> (n, D) embeddings, one packed launch sequence (no padding, no masks)."""
+        lengths = [int(c.shape[0]) for c in clips]
+        return self.fingerprint_packed(torch.cat([c.cuda() for c in clips], dim=0), lengths)
+
+    # ------------------------------------------------------------------ reference-compatible forward
+    def forward(self, video: torch.Tensor, return_features: bool = False):
+        """Same contract as model.py:272-298, including the `(B,3,T,H,W)` layout sniff on `shape[1] == 3`."""
+        if video.dim() != 5:
+            raise ValueError(f"expected a 5-D video tensor, got shape {tuple(video.shape)}")
+        if video.shape[1] == 3:  # reference quirk: a (B,T=3,3,H,W) input is also re-interpreted (model.py:283)
+            video = video.permute(0, 2, 1, 3, 4)
+        B, T = int(video.shape[0]), int(video.shape[1])
+        frames = video.reshape(B * T, *video.shape[2:])
+        out = self.fingerprint_packed(frames, [T] * B, return_features=return_features)
+        if return_features:
+            emb, feats = out
+            return emb, feats.view(B, T, 256)
+        return out
+
+    def compute_loss(self, *a, **k):
+        raise NotImplementedError("training (model.py:300-390) is outside the B200 inference hot path")
+
+
+def create_model(model_type: str = "attention", **kwargs) -> nn.Module:
+    """Factory with the reference's signature and error behaviour (model.py:585-610)."""
+    if model_type == "attention":
+        return VideoFingerprintAttention(
+            spatial_dim=kwargs.get("spatial_dim", 128),
+            temporal_dim=kwargs.get("temporal_dim", 256),
+            embedding_dim=kwargs.get("embedding_dim", 256),
+            num_attention_blocks=kwargs.get("num_attention_blocks", 4),
+        )
+    if model_type in ("3d", "cnn3d"):
+        raise NotImplementedError("the 3-D CNN model (model.py:393-582) is outside the B200 hot path (SURVEY.md section 8f)")
+    raise ValueError(f"Unknown model type: {model_type}")
