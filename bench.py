@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Headline benchmark of the B200 duplicate-detection hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): batched fingerprint forward of 10 000 synthetic clips x 64 frames @ 64x64
+per GPU, bf16 frames resident in HBM, random-init weights of the reference architecture. One "step" = one
+pass of `model.fingerprint_packed` over all clips of the rank. Launched under torchrun for N > 1 (one rank
+per GPU, clips sharded, no data-path collective in the forward => weak scaling).
+
+One JSON line on stdout (rank 0): value = whole-job videos/s (device-resident inputs), `e2e` = the same metric
+through the public API with HOST (pinned) uint8 frames, host<->device copies inside the timed region,
+`roofline` for the dominant kernel (per-stage CUDA-event times from the library's stage profiler),
+`cpu_baseline` = the oracle's reference-semantics B=1 loop on the box's host cores, `join` = the all-pairs
+cosine threshold join on synthetic unit vectors with planted duplicates (second half of the BASELINE metric).
+`--impl reference` times the reference algorithm's CPU path (oracle port; the reference itself is not
+installable on the GPU box) on the same config.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_CLIPS = 10_000
+T_FRAMES = 64
+FLOPS_PER_CLIP = 39_806_976 * T_FRAMES + 4096 * T_FRAMES * T_FRAMES + 524_288
+METRIC = "fingerprint videos/s (64 frames@64^2)"
+
+# algorithmic FLOPs per clip of each profiled stage (2 FLOP per MAC), T = 64
+_T = T_FRAMES
+STAGE_FLOPS = {
+    "conv1_stem": 2 * 1024 * 32 * 75 * _T,
+    "conv2_igemm": 2 * 256 * 64 * 288 * _T,
+    "conv3_igemm": 2 * 64 * 128 * 576 * _T,
+    "conv4_igemm_pool": 2 * 16 * 256 * 1152 * _T,
+    "token_embed_gemm": 2 * (256 * 128 + 128 * 256) * _T,
+    "qkv_gemm": 4 * 2 * 256 * 768 * _T,
+    "attention": 4 * 4 * _T * _T * 256,
+    "out_proj_gemm": 4 * 2 * 256 * 256 * _T,
+    "mlp1_gemm_gelu": 4 * 2 * 256 * 1024 * _T,
+    "mlp2_gemm": 4 * 2 * 1024 * 256 * _T,
+    "pool_logits_gemm": 2 * 256 * 256 * _T,
+}
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=float(p["hbm_gbs"]), tc_burst=float(p["bf16_tflops"]), tc_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    except Exception:
+        return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            )
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def dist_setup(n_gpus: int):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x: float, world: int, dev) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's --device cpu path: B=1 forward loop, fingerprint.py:244-249)
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_rate(budget_s: float, max_clips: int):
+    from oracle.forward_oracle import forward_oracle
+    from oracle.weights import make_state_dict
+
+    sd = make_state_dict(0, "default")
+    g = torch.Generator().manual_seed(4321)
+    clip = torch.rand((1, T_FRAMES, 3, 64, 64), generator=g)
+    forward_oracle(sd, clip)  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while n < max_clips and (time.perf_counter() - t0 < budget_s or n < 4):
+        forward_oracle(sd, clip)
+        n += 1
+    dt = time.perf_counter() - t0
+    return n / dt, n, dt
+
+
+def run_reference(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = torch.get_num_threads()
+    per_step = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_reference_rate(per_step / 4, 64)
+    rates, clips, secs = [], 0, 0.0
+    for _ in range(args.steps):
+        r, n, dt = cpu_reference_rate(per_step, 512)
+        rates.append(r)
+        clips += n
+        secs += dt
+    value = clips / secs
+    sample = f"{clips} clips x {T_FRAMES} frames in {secs:.1f}s, B=1 forwards (oracle port of the reference CPU path; the reference itself cannot be shipped to the GPU box)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "videos/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * secs / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": f"fingerprint forward, {T_FRAMES} frames @ 64x64 per clip, bounded sample of the 10k-clip workload"},
+        "cpu_baseline": {"value": value, "unit": "videos/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "world_size_env": world,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def make_join_data(n: int, dev, seed: int = 11):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    E = torch.randn((n, 256), generator=g, device=dev)
+    E = E / E.norm(dim=1, keepdim=True)
+    n_dup = n // 50
+    src = torch.randint(0, n, (n_dup,), generator=g, device=dev)
+    dst = torch.randint(0, n, (n_dup,), generator=g, device=dev)
+    sigma = torch.tensor([0.0, 0.005, 0.0145, 0.0205, 0.03], device=dev)[torch.randint(0, 5, (n_dup,), generator=g, device=dev)]
+    v = E[src] + sigma[:, None] * torch.randn((n_dup, 256), generator=g, device=dev)
+    E[dst] = v / v.norm(dim=1, keepdim=True)
+    return E.contiguous()
+
+
+def run_ours(args):
+    import video_fingerprint_b200 as vfp
+    from video_fingerprint_b200 import _native
+
+    world, rank, local = dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    lib = _native.load()
+    peaks = load_peaks()
+
+    n_clips = args.clips
+    torch.manual_seed(0)
+    model = vfp.create_model("attention").eval()
+    model.frames_per_pass = args.frames_per_pass
+    lengths = [T_FRAMES] * n_clips
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    frames = torch.empty((n_clips * T_FRAMES, 3, 64, 64), dtype=torch.bfloat16, device=dev)
+    chunk = 64 * T_FRAMES
+    for s in range(0, frames.shape[0], chunk):  # generate in slices: torch.rand has no bf16 generator path for 15 GB at once
+        e = min(frames.shape[0], s + chunk)
+        frames[s:e] = torch.rand((e - s, 3, 64, 64), generator=g, device=dev, dtype=torch.float32).to(torch.bfloat16)
+    torch.cuda.synchronize()
+
+    def step():
+        return model.fingerprint_packed(frames, lengths)
+
+    for _ in range(max(3, args.warmup)):
+        emb = step()
+    barrier(world)
+    stage_ms = (C.c_double * 32)()
+    launches = C.c_uint64(0)
+    lib.vfp_profile_read(stage_ms, 32, C.byref(launches), 1)  # reset the launch counter
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier(world)
+    ev0.record()
+    for _ in range(args.steps):
+        emb = step()
+    ev1.record()
+    barrier(world)
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    lib.vfp_profile_read(stage_ms, 32, C.byref(launches), 1)
+    gpu_launches = int(launches.value)
+    # per-kernel times: one more step with the library's stage profiler on (CUDA events between the stages,
+    # on the launching stream); kept out of the timed region because draining events stalls the launch thread
+    lib.vfp_profile_enable(1)
+    emb = step()
+    torch.cuda.synchronize()
+    lib.vfp_profile_read(stage_ms, 32, C.byref(launches), 1)
+    lib.vfp_profile_enable(0)
+    ms = max_over_ranks(ms, world, dev)
+    value = world * n_clips * args.steps / (ms / 1000.0)
+    n_stage = lib.vfp_profile_num_stages()
+    stages = {lib.vfp_profile_stage_name(i).decode(): stage_ms[i] for i in range(n_stage)}
+
+    # ---- end-to-end through the public API with host uint8 frames (pinned), copies inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        pool_clips = min(n_clips, 1000)
+        host = torch.empty((pool_clips * T_FRAMES, 3, 64, 64), dtype=torch.uint8).pin_memory()
+        host.random_(0, 256)
+        sub = min(pool_clips, 500)  # clips per H2D chunk (two device buffers, copy of chunk i+1 overlaps compute of i)
+        dbuf = [torch.empty((sub * T_FRAMES, 3, 64, 64), dtype=torch.uint8, device=dev) for _ in range(2)]
+        out_host = torch.empty((n_clips, 256), dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+
+        def e2e_step():
+            done, i = 0, 0
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+            free = [torch.cuda.Event(), torch.cuda.Event()]
+            for ev in free:
+                ev.record(main)
+            while done < n_clips:
+                n = min(sub, n_clips - done)
+                off = (done % pool_clips)
+                if off + n > pool_clips:
+                    off = 0
+                b = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[b])
+                    dbuf[b][: n * T_FRAMES].copy_(host[off * T_FRAMES : (off + n) * T_FRAMES], non_blocking=True)
+                    ready[b].record(copy_stream)
+                main.wait_event(ready[b])
+                e = model.fingerprint_packed(dbuf[b][: n * T_FRAMES], [T_FRAMES] * n)
+                out_host[done : done + n].copy_(e, non_blocking=True)
+                free[b].record(main)
+                done += n
+                i += 1
+            main.synchronize()
+
+        e2e_step()
+        barrier(world)
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier(world)
+        dt = max_over_ranks(time.perf_counter() - t0, world, dev)
+        e2e = {
+            "value": world * n_clips * e2e_steps / dt, "unit": "videos/s",
+            "h2d_bytes_per_step": n_clips * T_FRAMES * 12288, "d2h_bytes_per_step": n_clips * 256 * 4,
+            "input": "uint8 frames in pinned host memory, 500-clip chunks double-buffered on a copy stream", "steps": e2e_steps,
+        }
+        del dbuf, host
+
+    # ---- similarity join (second half of the BASELINE metric) ----
+    join = None
+    if not args.no_join:
+        n_join = args.join_n
+        E = make_join_data(n_join, dev)
+        row0 = 0
+        ii, jj, ss = vfp.threshold_join_device(E, 0.95)  # warm-up + sizes
+        cap = int(ii.numel()) + 4096
+        torch.cuda.synchronize()
+        barrier(world)
+        j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        j0.record()
+        reps = 3
+        for _ in range(reps):
+            ii, jj, ss = vfp.threshold_join_device(E, 0.95, capacity=cap)
+        j1.record()
+        torch.cuda.synchronize()
+        jms = max_over_ranks(j0.elapsed_time(j1) / reps, world, dev)
+        gpairs = world * (n_join * n_join) / (jms / 1000.0) / 1e9
+        tfl = gpairs * 512 / 1000.0 / world
+        join = {
+            "value": gpairs, "unit": "Gpairs/s", "n": n_join, "threshold": 0.95, "pairs_found": int(ii.numel()), "ms": jms,
+            "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tc_burst"], "unit": "TFLOP/s", "frac": tfl / peaks["tc_burst"], "traffic": None},
+            "note": "each rank joins its own N x N (replicas); the sharded all-gather join is exercised by tests/test_sharding.py",
+        }
+        del E
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel ----
+    dom = max((k for k in stages if k in STAGE_FLOPS), key=lambda k: stages[k])
+    launches_per_step = -(-n_clips * T_FRAMES // args.frames_per_pass)
+    dom_ms = stages[dom]
+    achieved = STAGE_FLOPS[dom] * n_clips / (dom_ms / 1000.0) / 1e12
+    roofline = {
+        "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tc_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tc_sustained"],
+        "traffic": None, "peak_source": f"{peaks['source']} (sustained bf16, kernel timed inside a long step)",
+        "launches_per_step": launches_per_step, "ms_per_step_in_kernel": dom_ms,
+        "whole_step": {"achieved": value / world * FLOPS_PER_CLIP / 1e12, "frac": value / world * FLOPS_PER_CLIP / 1e12 / peaks["tc_sustained"], "unit": "TFLOP/s"},
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": "videos/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"batched fingerprint forward: {n_clips} synthetic clips x {T_FRAMES} frames @ 64x64 per GPU, bf16 frames resident in HBM, random-init weights (BASELINE configs[1])",
+            "frames_per_pass": args.frames_per_pass, "l2": f"inputs ({n_clips * T_FRAMES * 24576 / 1e9:.1f} GB) and per-pass activations exceed the 126 MB L2; no flush needed",
+            "parallelism": f"clips sharded over {world} GPU(s), no data-path collective",
+        },
+        "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "stage_ms_per_step": stages, "join": join, "clocks": clocks,
+    }
+    if not args.no_cpu and world >= 1:
+        r, n, dt = cpu_reference_rate(args.cpu_seconds, 2048)
+        line["cpu_baseline"] = {
+            "value": r, "unit": "videos/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} clips x {T_FRAMES} frames in {dt:.1f}s, B=1 forward loop of oracle/forward_oracle.py (restatement of the reference --device cpu path) on host cores",
+        }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=N_CLIPS)
+    ap.add_argument("--frames-per-pass", type=int, default=8192)
+    ap.add_argument("--join-n", type=int, default=262_144)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-join", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    run_ours(args)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

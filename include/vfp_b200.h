@@ -101,6 +101,15 @@ int vfp_topk_ip(const float* q, const float* db, int64_t n_q, int64_t n_db, int 
                 float screen_margin, float* out_s, int64_t* out_idx, uint64_t* flags_out, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* Stage profiler (measurement hook, used by bench.py): when enabled, vfp_forward records CUDA events between
+ * its stages on the caller's stream. vfp_profile_read synchronises on the last event and returns the accumulated
+ * milliseconds per stage (vfp_profile_num_stages entries, names via vfp_profile_stage_name) and the number of
+ * kernels vfp_forward / vfp_join_threshold / vfp_topk_ip have launched since the last reset. Not thread-safe. */
+int vfp_profile_enable(int on);
+int vfp_profile_num_stages(void);
+const char* vfp_profile_stage_name(int i);
+int vfp_profile_read(double* stage_ms, int n_stages, uint64_t* launches, int reset);
+
 /* Reads and clears the device-side error word set by a kernel watchdog (0 = none). Synchronises. */
 unsigned int vfp_device_error_word(void);
 

@@ -1,0 +1,124 @@
+"""CPU: host-side logic of the package (no device compute): grouping, JSON schema, checkpoint layout, the
+C-ABI library's exported symbols, and the "fail loudly without a GPU" contract."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import video_fingerprint_b200 as vfp
+from oracle import join_oracle
+from oracle.weights import make_state_dict, state_dict_digest, state_spec
+from video_fingerprint_b200 import _native
+from video_fingerprint_b200.sharding import partition_clips, row_block
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_state_dict_layout_is_the_reference_layout():
+    m = vfp.create_model("attention")
+    sd = m.state_dict()
+    spec = state_spec()
+    assert list(sd.keys()) == [k for k, _, _ in spec]
+    for k, shape, kind in spec:
+        assert tuple(sd[k].shape) == tuple(shape), k
+        assert sd[k].dtype == (torch.int64 if kind == "bn_count" else torch.float32), k
+    m.load_state_dict(make_state_dict(3, "stress"), strict=True)
+
+
+def test_default_init_reproduces_reference_init(manifest):
+    """torch.manual_seed(0); create_model("attention") must give the weights the reference gives (BASELINE cfg 1)."""
+    torch.manual_seed(0)
+    m = vfp.create_model("attention")
+    assert state_dict_digest(m.state_dict()) == manifest["cfg1_refinit"]["weights_sha256"]
+    assert len(m.state_dict()) == manifest["cfg1_refinit"]["keys"]
+
+
+def test_factory_error_behaviour():
+    with pytest.raises(ValueError, match="Unknown model type"):
+        vfp.create_model("nope")
+    with pytest.raises(NotImplementedError):
+        vfp.create_model("3d")
+    m = vfp.create_model("attention", embedding_dim=128, num_attention_blocks=2, frame_stride=32)  # extra kwargs ignored
+    assert m.state_dict()["final_projection.3.weight"].shape == (128, 256)
+    assert not any(k.startswith("attention_blocks.2.") for k in m.state_dict())
+
+
+def test_grouping_matches_oracle_on_random_pair_sets():
+    rng = np.random.default_rng(0)
+    for trial in range(20):
+        n = int(rng.integers(2, 60))
+        E = rng.standard_normal((n, 8)).astype(np.float32)
+        E /= np.linalg.norm(E, axis=1, keepdims=True)
+        if trial % 3 == 0:
+            E *= rng.uniform(0.7, 1.0, size=(n, 1)).astype(np.float32)  # self-similarity may drop below thr
+        thr = float(rng.uniform(0.2, 0.9))
+        pi, pj, ps = join_oracle.threshold_pairs(E, thr)
+        assert vfp.group_pairs_direct(n, pi, pj, ps) == join_oracle.group_direct(n, pi, pj, ps)
+        S, I = join_oracle.topk_inner_product(E, E, min(5, n))
+        assert vfp.group_pairs_topk(S, I, thr) == join_oracle.group_topk(S, I, thr)
+    assert vfp.group_pairs_direct(5, np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float32)) == []
+
+
+def test_partition_and_row_blocks():
+    lengths = [300, 16, 16, 200, 100, 100, 64, 64, 64, 10]
+    for world in (1, 2, 4, 8):
+        parts = partition_clips(lengths, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(lengths)))
+        loads = [sum(lengths[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(lengths)
+        blocks = [row_block(1000, world, r) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == 1000
+        assert all(b[1] == blocks[i + 1][0] for i, b in enumerate(blocks[:-1]))
+        assert all(b[0] % 128 == 0 for b in blocks)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "vfp_b200.h")).read()
+    declared = set(re.findall(r"\b(vfp_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_native.EXPORTED_SYMBOLS)
+    assert os.path.exists(_native.LIB_PATH), "build the library first: python -m video_fingerprint_b200.build"
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _native.load().vfp_abi_version() == _native.ABI_VERSION
+    # pure host-side entry points are callable without a GPU
+    assert _native.load().vfp_forward_workspace_bytes(64, 1) > 64 * 100_000
+    assert _native.load().vfp_join_workspace_bytes(1000, 1000, 4096) >= 2 * 1000 * 512
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_path_fails_loudly_without_gpu():
+    m = vfp.create_model("attention").eval()
+    with pytest.raises(_native.NativeError, match="no CUDA device"):
+        m(torch.zeros(1, 10, 3, 64, 64))
+    with pytest.raises(_native.NativeError, match="no CUDA device"):
+        vfp.threshold_join(np.zeros((4, 256), np.float32), 0.9)
+    with pytest.raises(_native.NativeError, match="no CUDA device"):
+        vfp.VideoFingerprintScanner(model=m)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "video_fingerprint_b200")
+    for name in os.listdir(pkg):
+        if name.endswith(".py"):
+            src = open(os.path.join(pkg, name)).read()
+            assert "oracle" not in src.replace("the oracle", "").replace("inject the oracle", ""), name
+
+
+def test_save_results_schema(tmp_path):
+    scanner = vfp.VideoFingerprintScanner.__new__(vfp.VideoFingerprintScanner)
+    scanner.config, scanner.model_type = {"model_type": "attention"}, "attention"
+    e = np.ones(256, np.float32) / 16
+    fps = {"a.mp4": {"embedding": e, "path": "a.mp4", "name": "a.mp4", "size": 5, "file_hash": "h", "embedding_norm": np.float32(1.0)}}
+    groups = [[dict(fps["a.mp4"], similarity=1.0, exact_duplicate=False)]]
+    out = tmp_path / "r.json"
+    scanner.save_results(fps, groups, out)  # the reference raises TypeError here (np.float32 / ndarray members)
+    data = json.loads(out.read_text())
+    assert set(data) == {"metadata", "fingerprints", "duplicate_groups"}
+    assert set(data["metadata"]) == {"scan_date", "total_videos", "duplicate_groups", "model_config", "model_type"}
+    assert isinstance(data["fingerprints"]["a.mp4"]["embedding"], list) and len(data["fingerprints"]["a.mp4"]["embedding"]) == 256
+    assert data["duplicate_groups"][0][0]["similarity"] == 1.0

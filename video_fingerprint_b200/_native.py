@@ -29,6 +29,10 @@ EXPORTED_SYMBOLS = (
     "vfp_topk_workspace_bytes",
     "vfp_topk_ip",
     "vfp_device_error_word",
+    "vfp_profile_enable",
+    "vfp_profile_num_stages",
+    "vfp_profile_stage_name",
+    "vfp_profile_read",
 )
 
 
@@ -79,6 +83,14 @@ def load() -> C.CDLL:
     lib.vfp_topk_workspace_bytes.argtypes = [i64, i64, i32]
     lib.vfp_topk_ip.restype = i32
     lib.vfp_topk_ip.argtypes = [vp, vp, i64, i64, i32, i32, f32, vp, vp, vp, vp, sz, vp]
+    lib.vfp_profile_enable.restype = i32
+    lib.vfp_profile_enable.argtypes = [i32]
+    lib.vfp_profile_num_stages.restype = i32
+    lib.vfp_profile_num_stages.argtypes = []
+    lib.vfp_profile_stage_name.restype = C.c_char_p
+    lib.vfp_profile_stage_name.argtypes = [i32]
+    lib.vfp_profile_read.restype = i32
+    lib.vfp_profile_read.argtypes = [vp, i32, vp, i32]
     lib.vfp_device_error_word.restype = C.c_uint
     lib.vfp_device_error_word.argtypes = []
     if lib.vfp_abi_version() != ABI_VERSION:

@@ -38,6 +38,51 @@ int fail_cuda(const char* what, cudaError_t e) {
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 constexpr float kBnEps = 1e-5f;
+
+// ---------------------------------------------------------------------------------------------
+// optional stage profiler: CUDA events recorded between the stages of a forward pass, on the caller's
+// stream (bench.py reads per-kernel time from here; it is off unless vfp_profile_enable(1) was called)
+// ---------------------------------------------------------------------------------------------
+enum Stage : int {
+  kStConv1 = 0, kStConv2, kStConv3, kStConv4, kStTokEmbed, kStTemporalConv, kStLayerNorm, kStQkv, kStAttention,
+  kStOutProj, kStMlp1, kStMlp2, kStPoolGemm, kStPool, kStFinal, kStMisc, kNumStages
+};
+const char* const kStageNames[kNumStages] = {"conv1_stem", "conv2_igemm", "conv3_igemm", "conv4_igemm_pool", "token_embed_gemm",
+                                             "temporal_conv", "layernorm", "qkv_gemm", "attention", "out_proj_gemm",
+                                             "mlp1_gemm_gelu", "mlp2_gemm", "pool_logits_gemm", "temporal_pool",
+                                             "final_projection", "misc"};
+struct Profiler {
+  bool enabled = false;
+  std::vector<cudaEvent_t> pool;
+  std::vector<std::pair<int, cudaEvent_t>> marks;  // (stage that ENDS at this event, event); stage -1 = pass start
+  size_t next = 0;
+  double ms[kNumStages] = {0};
+  unsigned long long launches = 0;
+  void mark(int stage, cudaStream_t st) {
+    if (!enabled) return;
+    if (next == pool.size()) {
+      cudaEvent_t e;
+      cudaEventCreate(&e);
+      pool.push_back(e);
+    }
+    cudaEvent_t e = pool[next++];
+    cudaEventRecord(e, st);
+    marks.emplace_back(stage, e);
+  }
+  void drain() {
+    if (marks.empty()) return;
+    cudaEventSynchronize(marks.back().second);
+    for (size_t i = 1; i < marks.size(); ++i) {
+      if (marks[i].first < 0) continue;
+      float t = 0.f;
+      cudaEventElapsedTime(&t, marks[i - 1].second, marks[i].second);
+      ms[marks[i].first] += t;
+    }
+    marks.clear();
+    next = 0;
+  }
+};
+Profiler g_prof;
 const int kTemporalKernels[4] = {3, 5, 7, 11};
 
 struct AttnBlockWeights {
@@ -218,6 +263,24 @@ int vfp_device_sm_count(void) {
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   return sms;
+}
+
+int vfp_profile_enable(int on) {
+  g_prof.drain();
+  g_prof.enabled = on != 0;
+  return 0;
+}
+int vfp_profile_num_stages(void) { return kNumStages; }
+const char* vfp_profile_stage_name(int i) { return (i >= 0 && i < kNumStages) ? kStageNames[i] : ""; }
+int vfp_profile_read(double* stage_ms, int n_stages, uint64_t* launches, int reset) {
+  g_prof.drain();
+  for (int i = 0; i < n_stages && i < kNumStages; ++i) stage_ms[i] = g_prof.ms[i];
+  if (launches) *launches = g_prof.launches;
+  if (reset) {
+    for (int i = 0; i < kNumStages; ++i) g_prof.ms[i] = 0;
+    g_prof.launches = 0;
+  }
+  return 0;
 }
 
 unsigned int vfp_device_error_word(void) {
@@ -435,9 +498,12 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   int max_T = 0;
   for (int i = 0; i <= C; ++i) cu_rel[i] = (int32_t)(cu_host[c0 + i] - f0);
   for (int i = 0; i < C; ++i) max_T = std::max(max_T, cu_rel[i + 1] - cu_rel[i]);
+  g_prof.mark(-1, st);
+  g_prof.launches += 12 + 7 * (unsigned long long)w->n_attn;
   VFP_CUDA(cudaMemcpyAsync(d_cu, cu_rel.data(), (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, st));
   // cu_rel is pageable: the copy is staged before the call returns, so the vector may die with this scope.
   token_map_kernel<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(d_cu, C, (int)F, tok_pos, tok_len);
+  g_prof.mark(kStMisc, st);
 
   // ---- frame encoder ----
   const int sms = device_sm_count();
@@ -445,6 +511,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     const long long grid = std::min<long long>(F, (long long)sms * 8);
     conv1_stem_kernel<<<(unsigned)grid, kC1Threads, 0, st>>>(frames_base + (size_t)f0 * frame_bytes, frame_dtype, F,
                                                             w->c1_wpack, w->c1_bias, c1a);
+    g_prof.mark(kStConv1, st);
   }
   CUtensorMap ta;
   {  // conv2: 32x32x32 -> 16x16x64, tile = 8 output rows x 16 cols of one frame
@@ -455,6 +522,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     EpiBiasAct::Params ep{};
     ep.bias = w->c2_b; ep.out_bf16 = c2a; ep.ld_out = 64; ep.M = (int)(F * 256); ep.N = 64; ep.act = 1;
     VFP_CUDA((launch_gemm<64, 32, 8, EpiBiasAct>(ta, w->tm_c2, s, ep, st)));
+    g_prof.mark(kStConv2, st);
   }
   {  // conv3: 16x16x64 -> 8x8x128, tile = 2 frames
     if (make_tmap_conv_s2_bf16(&ta, c2a, F, 16, 16, 64, 64, 8, 8, 2)) return fail("tensor map encode failed (conv3)");
@@ -464,6 +532,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     EpiBiasAct::Params ep{};
     ep.bias = w->c3_b; ep.out_bf16 = c3a; ep.ld_out = 128; ep.M = (int)(F * 64); ep.N = 128; ep.act = 1;
     VFP_CUDA((launch_gemm<128, 64, 6, EpiBiasAct>(ta, w->tm_c3, s, ep, st)));
+    g_prof.mark(kStConv3, st);
   }
   {  // conv4: 8x8x128 -> 4x4x256 + ReLU + global average pool, tile = 8 frames
     if (make_tmap_conv_s2_bf16(&ta, c3a, F, 8, 8, 128, 64, 4, 4, 8)) return fail("tensor map encode failed (conv4)");
@@ -473,6 +542,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     EpiConvPool16::Params ep{};
     ep.bias = w->c4_b; ep.out_bf16 = feat; ep.frames = (int)F; ep.N = 256;
     VFP_CUDA((launch_gemm<256, 64, 4, EpiConvPool16>(ta, w->tm_c4, s, ep, st)));
+    g_prof.mark(kStConv4, st);
   }
   // ---- token embedding: x = Wtok feat + btok + pe[pos] ----
   auto token_gemm = [&](const __nv_bfloat16* A, int K, const CUtensorMap& tb, int N, const EpiBiasAct::Params& ep) -> int {
@@ -486,12 +556,14 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     EpiBiasAct::Params ep{};
     ep.bias = w->btok; ep.pe = w->pe; ep.token_pos = tok_pos; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
     if (token_gemm(feat, 256, w->tm_tok, kDim, ep)) return 1;
+    g_prof.mark(kStTokEmbed, st);
   }
   // ---- multi-scale temporal convolutions (residual) ----
   {
     const unsigned grid = (unsigned)((F + 7) / 8);
     temporal_conv_kernel<<<grid, 256, 0, st>>>(xa, tok_pos, tok_len, w->tc_w[0], w->tc_b[0], xb, (int)F);
     temporal_conv_kernel<<<grid, 256, 0, st>>>(xb, tok_pos, tok_len, w->tc_w[1], w->tc_b[1], xa, (int)F);
+    g_prof.mark(kStTemporalConv, st);
   }
   // ---- attention blocks ----
   const unsigned ln_grid = (unsigned)((F * 32 + 255) / 256);
@@ -504,27 +576,34 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   for (int b = 0; b < w->n_attn; ++b) {
     const AttnBlockWeights& a = w->attn[b];
     layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, a.ln1_w, a.ln1_b, xn, (int)F);
+    g_prof.mark(kStLayerNorm, st);
     {
       EpiBiasAct::Params ep{};
       ep.bias = a.bqkv; ep.out_bf16 = qkv; ep.ld_out = 3 * kDim; ep.M = (int)F; ep.N = 3 * kDim;
       if (token_gemm(xn, kDim, a.tm_qkv, 3 * kDim, ep)) return 1;
+      g_prof.mark(kStQkv, st);
     }
     attention_clip_kernel<<<dim3((unsigned)C, kHeads), 128, att_smem, st>>>(qkv, d_cu, att);
+    g_prof.mark(kStAttention, st);
     {
       EpiBiasAct::Params ep{};
       ep.bias = a.bo; ep.residual = xa; ep.ld_res = kDim; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
       if (token_gemm(att, kDim, a.tm_o, kDim, ep)) return 1;
+      g_prof.mark(kStOutProj, st);
     }
     layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, a.ln2_w, a.ln2_b, xn, (int)F);
+    g_prof.mark(kStLayerNorm, st);
     {
       EpiBiasAct::Params ep{};
       ep.bias = a.b1; ep.act = 2; ep.out_bf16 = hbuf; ep.ld_out = 4 * kDim; ep.M = (int)F; ep.N = 4 * kDim;
       if (token_gemm(xn, kDim, a.tm_w1, 4 * kDim, ep)) return 1;
+      g_prof.mark(kStMlp1, st);
     }
     {
       EpiBiasAct::Params ep{};
       ep.bias = a.b2; ep.residual = xa; ep.ld_res = kDim; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
       if (token_gemm(hbuf, 4 * kDim, a.tm_w2, kDim, ep)) return 1;
+      g_prof.mark(kStMlp2, st);
     }
   }
   if (features_out)
@@ -535,10 +614,14 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     EpiBiasAct::Params ep{};
     ep.bias = w->bpool; ep.act = 1; ep.out_f32 = logits; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
     if (token_gemm(xbf, kDim, w->tm_pool, kDim, ep)) return 1;
+    g_prof.mark(kStPoolGemm, st);
   }
   temporal_pool_kernel<<<(unsigned)C, 256, 0, st>>>(xa, logits, d_cu, pooled);
+  g_prof.mark(kStPool, st);
   final_projection_kernel<8><<<(unsigned)((C + 7) / 8), 256, 0, st>>>(pooled, w->w0t, w->b0, w->w3t, w->b3, w->embedding_dim,
                                                                    C, emb_out + (size_t)c0 * w->embedding_dim);
+  g_prof.mark(kStFinal, st);
+  if (g_prof.marks.size() > 4096) g_prof.drain();
   VFP_CUDA(cudaGetLastError());
   return 0;
 }
