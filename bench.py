@@ -334,7 +334,9 @@ def run_ours(args):
         return
     # ---- roofline of the dominant kernel ----
     dom = max((k for k in stages if k in STAGE_FLOPS), key=lambda k: stages[k])
-    launches_per_step = -(-n_clips * T_FRAMES // args.frames_per_pass)
+    token_passes = -(-n_clips * T_FRAMES // args.frames_per_pass)
+    conv_passes = -(-min(n_clips * T_FRAMES, args.frames_per_pass) // 16384) * token_passes
+    launches_per_step = conv_passes if dom.startswith("conv") else token_passes * (4 if dom.endswith("gemm") or dom in ("attention", "mlp1_gemm_gelu") else 1)
     dom_ms = stages[dom]
     achieved = STAGE_FLOPS[dom] * n_clips / (dom_ms / 1000.0) / 1e12
     roofline = {
@@ -369,7 +371,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=N_CLIPS)
-    ap.add_argument("--frames-per-pass", type=int, default=8192)
+    ap.add_argument("--frames-per-pass", type=int, default=1 << 20)
     ap.add_argument("--join-n", type=int, default=262_144)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--no-e2e", action="store_true")

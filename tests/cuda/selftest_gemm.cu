@@ -120,7 +120,7 @@ static int run_conv(int frames) {
   s.group_m = 8;
   s.n_tiles = COUT / BN;
   s.k_blocks = K / BK;
-  s.cblocks_per_tap = CIN / BK;
+  conv_taps_strided(&s, CIN / BK);
   int out_w = HOUT, out_h, n_box;
   if (PIX >= 128) {
     s.tiles_per_frame = PIX / 128;

@@ -1,5 +1,5 @@
 // Frame-encoder stem: Conv2d(3->32, k5, s2, p2) + folded BatchNorm + ReLU, planar CHW frames in
-// (u8 / bf16 / fp32), bf16 NHWC [frame][32][32][32] out.
+// (u8 / bf16 / fp32), bf16 out in space-to-depth NHWC: [frame][16][16][(oh%2*2 + ow%2)*32 + c].
 //
 // C_in = 3 gives 6-byte pixels, which neither the TMA im2col box nor a UMMA smem descriptor can address,
 // so this layer runs on the register-fragment tensor path (mma.sync m16n8k16, bf16 -> fp32): every thread
@@ -120,7 +120,10 @@ conv1_stem_kernel(const void* __restrict__ frames, int frame_dtype, long long n_
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a, bfrag[kh][nt]);
       }
-      const int p_lo = oh * 32 + ow0 + g;
+      // space-to-depth store: pixel (oh, ow) -> cell (oh/2, ow/2), channel block (oh%2)*2 + ow%2; conv2 then reads
+      // dense channel slices instead of every second pixel. Pixel +8 along W = cell +4 = +512 elements.
+      const int ow = ow0 + g;
+      const int p_lo = ((oh >> 1) * 16 + (ow >> 1)) * 4 + (oh & 1) * 2 + (ow & 1);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const float v0 = fmaxf(acc[nt][0] + bia[nt][0], 0.0f);
@@ -130,7 +133,7 @@ conv1_stem_kernel(const void* __restrict__ frames, int frame_dtype, long long n_
         __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1);
         __nv_bfloat162 hi = __floats2bfloat162_rn(v2, v3);
         *reinterpret_cast<__nv_bfloat162*>(out_f + p_lo * 32 + nt * 8 + 2 * tig) = lo;
-        *reinterpret_cast<__nv_bfloat162*>(out_f + (p_lo + 8) * 32 + nt * 8 + 2 * tig) = hi;
+        *reinterpret_cast<__nv_bfloat162*>(out_f + (p_lo + 16) * 32 + nt * 8 + 2 * tig) = hi;
       }
     }
     __syncthreads();  // before the next frame overwrites the tile

@@ -27,9 +27,11 @@ struct EpiBiasAct {
     int M, N;
     int act;  // 0 none, 1 relu, 2 gelu(erf)
   };
+  static constexpr int kPasses = 1;
+  static constexpr int kColumnSplit = 2;
   __device__ __forceinline__ void begin(const Params&, int, int, int) {}
   __device__ __forceinline__ void end(const Params&, int, int, int) {}
-  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32]) {
+  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int /*pass*/) {
     const long long grow = (long long)mt * kBlockMRows + row;
     if (grow >= p.M || col0 >= p.N) return;
     float x[32];
@@ -97,9 +99,11 @@ struct EpiConvPool16 {
     __nv_bfloat16* out_bf16;  // [frames][N]
     int frames, N;
   };
+  static constexpr int kPasses = 1;
+  static constexpr int kColumnSplit = 2;
   __device__ __forceinline__ void begin(const Params&, int, int, int) {}
   __device__ __forceinline__ void end(const Params&, int, int, int) {}
-  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32]) {
+  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int /*pass*/) {
     const int lane = threadIdx.x & 31;
     float x[32];
 #pragma unroll
@@ -129,6 +133,47 @@ struct EpiConvPool16 {
 };
 
 // -------------------------------------------------------------------------------------------
+// last layer of the head: e = acc + bias, out = e / max(||e||_2, 1e-12)  (F.normalize, model.py:294).
+// BLOCK_N covers the whole embedding row, so the thread that owns the row owns the whole reduction:
+// pass 0 accumulates the squared norm, pass 1 re-reads the accumulator from TMEM and writes the scaled row.
+// -------------------------------------------------------------------------------------------
+struct EpiBiasL2Norm {
+  struct Params {
+    const float* bias;  // [N]
+    float* out_f32;     // [M][N]
+    int M, N;           // N <= BLOCK_N, multiple of 32
+  };
+  static constexpr int kPasses = 2;
+  static constexpr int kColumnSplit = 1;
+  float sumsq;
+  __device__ __forceinline__ void begin(const Params&, int, int, int) { sumsq = 0.f; }
+  __device__ __forceinline__ void end(const Params&, int, int, int) {}
+  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int pass) {
+    const long long grow = (long long)mt * 128 + row;
+    if (grow >= p.M || col0 >= p.N) return;
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+      x[i] = __uint_as_float(v[i]) + b.x;
+      x[i + 1] = __uint_as_float(v[i + 1]) + b.y;
+      x[i + 2] = __uint_as_float(v[i + 2]) + b.z;
+      x[i + 3] = __uint_as_float(v[i + 3]) + b.w;
+    }
+    if (pass == 0) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sumsq += x[i] * x[i];
+    } else {
+      const float inv = 1.0f / fmaxf(sqrtf(sumsq), 1e-12f);
+      float* o = p.out_f32 + grow * p.N + col0;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<float4*>(o + i) = make_float4(x[i] * inv, x[i + 1] * inv, x[i + 2] * inv, x[i + 3] * inv);
+    }
+  }
+};
+
+// -------------------------------------------------------------------------------------------
 // similarity-join screen: emit (i, j, s) for every accumulator >= thr (bf16 inputs, fp32 accumulate).
 // Survivors are rare, so one global atomic per hit is cheaper than any staging. `count` keeps
 // counting past `capacity` so the caller can size a retry.
@@ -144,9 +189,11 @@ struct EpiJoinThreshold {
     unsigned long long* count;
     long long capacity;
   };
+  static constexpr int kPasses = 1;
+  static constexpr int kColumnSplit = 2;
   __device__ __forceinline__ void begin(const Params&, int, int, int) {}
   __device__ __forceinline__ void end(const Params&, int, int, int) {}
-  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32]) {
+  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int /*pass*/) {
     const long long qi = (long long)mt * 128 + row;
     if (qi >= p.q_rows) return;
     float m = __uint_as_float(v[0]);

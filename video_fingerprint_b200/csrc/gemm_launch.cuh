@@ -32,7 +32,7 @@ inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, con
   const int total = shape.m_tiles * shape.n_tiles;
   if (total <= 0) return cudaSuccess;
   const int grid = total < device_sm_count() ? total : device_sm_count();
-  kernel<<<grid, kGemmThreads, L::kTotal, stream>>>(ta, tb, shape, ep);
+  kernel<<<grid, gemm_threads<BLOCK_N, Epi>(), L::kTotal, stream>>>(ta, tb, shape, ep);
   return cudaGetLastError();
 }
 
@@ -46,8 +46,35 @@ inline GemmShape plain_shape(long long M, int N, int K, int block_n, int block_k
   s.tiles_per_frame = 1;
   s.frames_per_tile = 1;
   s.tile_out_rows = 0;
-  s.cblocks_per_tap = 1;
+  s.h_mul = 0;
   return s;
+}
+
+// 3x3 / stride-2 / pad-1 convolution read through a stride-2 TMA box: K block kb = tap (kh, kw) x channel slice
+inline void conv_taps_strided(GemmShape* s, int cblocks_per_tap) {
+  s->h_mul = 2;
+  for (int kb = 0; kb < 9 * cblocks_per_tap; ++kb) {
+    const int tap = kb / cblocks_per_tap, kh = tap / 3, kw = tap % 3;
+    s->tap_c_blk[kb] = (signed char)(kb % cblocks_per_tap);
+    s->tap_w[kb] = (signed char)(kw - 1);
+    s->tap_h[kb] = (signed char)(kh - 1);
+  }
+}
+
+// The same convolution over a space-to-depth input [frame][H/2][W/2][(sh*2+sw)*C + c]: it becomes a 2x2 /
+// stride-1 window over cells, every tap reads ONE dense channel slice of a cell (no strided traversal).
+// tap k in {0,1,2} -> input row 2*o + k - 1 = cell (o + d), sub-row s with (d, s) = (-1,1), (0,0), (0,1).
+inline void conv_taps_space_to_depth(GemmShape* s, int cblocks_per_subpixel) {
+  s->h_mul = 1;
+  const int d[3] = {-1, 0, 0}, sub[3] = {1, 0, 1};
+  int kb = 0;
+  for (int kh = 0; kh < 3; ++kh)
+    for (int kw = 0; kw < 3; ++kw)
+      for (int cb = 0; cb < cblocks_per_subpixel; ++cb, ++kb) {
+        s->tap_c_blk[kb] = (signed char)((sub[kh] * 2 + sub[kw]) * cblocks_per_subpixel + cb);
+        s->tap_w[kb] = (signed char)d[kw];
+        s->tap_h[kb] = (signed char)d[kh];
+      }
 }
 
 }  // namespace vfp

@@ -4,7 +4,7 @@
 //
 //   warp 0      : TMA producer (one lane)            global -> swizzled smem ring, mbarrier complete_tx
 //   warp 1      : TMEM allocator + UMMA issuer (one lane), tcgen05.commit releases smem stages
-//   warps 2..5  : epilogue; each warp owns one 32-lane quarter of the 128 accumulator rows and
+//   warps 2..5(9): epilogue; each warp owns one 32-lane quarter of the 128 accumulator rows (x half the columns) and
 //                 drains them with tcgen05.ld while the issuer already fills the other accumulator
 //                 buffer (two BLOCK_N-column buffers in TMEM).
 //
@@ -16,8 +16,14 @@
 
 namespace vfp {
 
-constexpr int kGemmThreads = 192;
 constexpr int kBlockM = 128;
+
+// Epilogues that only do column-local work let two warps share one TMEM lane quarter (each takes half of the
+// BLOCK_N columns); row-reducing epilogues keep one thread per row.
+template <int BLOCK_N, class Epilogue>
+constexpr int gemm_column_split() { return (Epilogue::kColumnSplit == 2 && BLOCK_N >= 64) ? 2 : 1; }
+template <int BLOCK_N, class Epilogue>
+constexpr int gemm_threads() { return 64 + 128 * gemm_column_split<BLOCK_N, Epilogue>(); }
 
 struct GemmShape {
   int m_tiles;     // number of 128-row tiles
@@ -25,11 +31,16 @@ struct GemmShape {
   int k_blocks;    // K / BLOCK_K
   int group_m;     // rasterisation: tiles are walked in groups of `group_m` row tiles (L2 reuse)
   // A operand addressing
-  int a_conv;           // 0: rows are GEMM rows; 1: 4-D strided box (C, W, H, frame)
+  int a_conv;           // 0: rows are GEMM rows; 1: 4-D box (C, W, H, frame) over an NHWC activation tensor
   int tiles_per_frame;  // conv: row tiles per frame (>=1) ...
   int frames_per_tile;  //       ... or frames per row tile (>=1)
   int tile_out_rows;    // conv: output rows (H) covered by one tile inside a frame
-  int cblocks_per_tap;  // conv: K blocks per filter tap (C_in / BLOCK_K)
+  int h_mul;            // conv: H coordinate of a tile = h_mul * first_output_row + tap_h[kb]
+  // conv: per-K-block box origin (channel offset, W offset, H offset). One K block = one filter tap
+  // (or a channel slice of it); the -1 entries address the zero halo the TMA unit fills in.
+  signed char tap_c_blk[18];  // channel offset in units of BLOCK_K
+  signed char tap_w[18];
+  signed char tap_h[18];
 };
 
 __device__ __forceinline__ void tile_coords(const GemmShape& s, int t, int& mt, int& nt) {
@@ -53,7 +64,7 @@ struct GemmSmemLayout {
 };
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, class Epilogue>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(gemm_threads<BLOCK_N, Epilogue>(), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmShape shape, const typename Epilogue::Params ep) {
   using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES>;
@@ -86,7 +97,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[i], 4 * gemm_column_split<BLOCK_N, Epilogue>());  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -120,11 +131,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
           if (shape.a_conv) {
-            const int tap = kb / shape.cblocks_per_tap;
-            const int cb = kb - tap * shape.cblocks_per_tap;
-            const int kh = tap / 3, kw = tap - kh * 3;
-            tma_load_4d(&tmap_a, &full_bar[stage], smem_a + stage * L::kABytes, cb * BLOCK_K, kw - 1,
-                        2 * oh0 + kh - 1, frame0);
+            tma_load_4d(&tmap_a, &full_bar[stage], smem_a + stage * L::kABytes, shape.tap_c_blk[kb] * BLOCK_K,
+                        shape.tap_w[kb], shape.h_mul * oh0 + shape.tap_h[kb], frame0);
           } else {
             tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * L::kABytes, kb * BLOCK_K, mt * kBlockM);
           }
@@ -164,8 +172,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     }
   } else {
     // ------------------------------ epilogue ------------------------------
+    constexpr int kSplit = gemm_column_split<BLOCK_N, Epilogue>();
+    constexpr int kColsPerWarp = BLOCK_N / kSplit;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = quarter * 32 + lane;
+    const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
     int local = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
       int mt, nt;
@@ -178,11 +189,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       Epilogue epi;
       epi.begin(ep, mt, nt, row);
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32(taddr + c, v);
-        tmem_ld_wait();
-        epi.chunk(ep, mt, nt * BLOCK_N + c, row, v);
+      for (int pass = 0; pass < Epilogue::kPasses; ++pass) {  // row-wise reductions re-read the accumulator
+#pragma unroll 1
+        for (int c = col_begin; c < col_begin + kColsPerWarp; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c, v);
+          tmem_ld_wait();
+          epi.chunk(ep, mt, nt * BLOCK_N + c, row, v, pass);
+        }
       }
       epi.end(ep, mt, nt, row);
       tc_fence_before();

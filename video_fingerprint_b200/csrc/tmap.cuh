@@ -50,22 +50,26 @@ inline int make_tmap_rows_bf16(CUtensorMap* out, const void* base, uint64_t rows
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
-// bf16 NHWC activation tensor [frames][H][W][C] read as the A operand of a 3x3 / stride-2 / pad-1
-// convolution: one box = (c_box channels) x (out_w outputs along W, every 2nd pixel) x (out_h outputs
-// along H, every 2nd pixel) x (n_box frames). Out-of-range coordinates (the -1 halo, frames past the
-// end) are zero-filled by the TMA unit.
-inline int make_tmap_conv_s2_bf16(CUtensorMap* out, const void* base, uint64_t frames, uint32_t H, uint32_t W,
-                                  uint32_t C, uint32_t c_box, uint32_t out_w, uint32_t out_h, uint32_t n_box) {
+// bf16 NHWC activation tensor [frames][H][W][C] read as the A operand of an implicit-GEMM convolution:
+// one box = (c_box channels) x (out_w positions along W) x (out_h positions along H) x (n_box frames), visiting
+// every `stride`-th pixel along W and H (stride 2 = the 3x3/stride-2 convolutions; stride 1 = a space-to-depth
+// input). Out-of-range coordinates (the -1 halo, frames past the end) are zero-filled by the TMA unit.
+inline int make_tmap_nhwc_bf16(CUtensorMap* out, const void* base, uint64_t frames, uint32_t H, uint32_t W, uint32_t C,
+                               uint32_t c_box, uint32_t out_w, uint32_t out_h, uint32_t n_box, uint32_t stride) {
   PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
   if (!enc) return 1;
   cuuint64_t gdim[4] = {C, W, H, frames};
   cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {c_box, out_w * 2, out_h * 2, n_box};
-  cuuint32_t estr[4] = {1, 2, 2, 1};
+  cuuint32_t box[4] = {c_box, out_w * stride, out_h * stride, n_box};
+  cuuint32_t estr[4] = {1, stride, stride, 1};
   CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for_row_bytes(c_box * 2),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 2;
+}
+inline int make_tmap_conv_s2_bf16(CUtensorMap* out, const void* base, uint64_t frames, uint32_t H, uint32_t W,
+                                  uint32_t C, uint32_t c_box, uint32_t out_w, uint32_t out_h, uint32_t n_box) {
+  return make_tmap_nhwc_bf16(out, base, frames, H, W, C, c_box, out_w, out_h, n_box, 2);
 }
 
 }  // namespace vfp

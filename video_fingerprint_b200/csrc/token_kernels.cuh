@@ -104,86 +104,149 @@ temporal_conv_kernel(const float* __restrict__ x, const int* __restrict__ tok_po
 }
 
 // ---------------------------------------------------------------------------------------------
-// Multi-head self-attention over one clip. grid = (clip, head); K and V of the head live in shared
-// memory as bf16; each thread owns one query row and runs an online softmax over the clip's keys.
-// qkv: [tokens][768] bf16 = [Q | K | V], head h = columns 32h..32h+31 of each (model.py:130-132, 143).
+// Multi-head self-attention over one clip (model.py:143), flash-style on the register-fragment tensor path
+// (mma.sync m16n8k16 bf16 -> fp32): head_dim 32 and T <= ~500 make every (clip, head) problem a few 64x64x32
+// tiles - far too small for a 128-row UMMA tile, and the whole stage is < 1 % of the forward FLOPs.
+// grid = (clip, head, 64-query block); 4 warps x 16 query rows; keys are walked in blocks of 64 with an online
+// softmax, so any clip length works. qkv: [tokens][768] bf16 = [Q | K | V], head h = columns 32h..32h+31.
 // ---------------------------------------------------------------------------------------------
+constexpr int kAttQ = 64;
+constexpr int kAttKeys = 64;
+constexpr int kAttKPitch = 40;             // bf16 per K row in smem: 32 + 8 pad -> conflict-free fragment loads
+constexpr int kAttVPitch = kAttKeys + 8;   // bf16 per V^T row
+
+__device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 __global__ void __launch_bounds__(128)
-attention_clip_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ cu, __nv_bfloat16* __restrict__ out) {
-  extern __shared__ __align__(16) uint8_t att_smem[];
+attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ cu, __nv_bfloat16* __restrict__ out) {
+  __shared__ __align__(16) __nv_bfloat16 Ks[kAttKeys * kAttKPitch];
+  __shared__ __align__(16) __nv_bfloat16 Vt[kHeadDim * kAttVPitch];
   const int clip = blockIdx.x, head = blockIdx.y;
   const int t0 = cu[clip];
   const int T = cu[clip + 1] - t0;
-  uint4* ks = reinterpret_cast<uint4*>(att_smem);   // [T][4] uint4 = 32 bf16 per key
-  uint4* vs = ks + (size_t)T * 4;
-  for (int i = threadIdx.x; i < T * 4; i += blockDim.x) {
-    const int t = i >> 2, c = i & 3;
-    const uint4* row = reinterpret_cast<const uint4*>(qkv + (size_t)(t0 + t) * (3 * kDim) + head * kHeadDim);
-    ks[i] = row[kDim / 8 + c];       // +256 bf16
-    vs[i] = row[2 * kDim / 8 + c];   // +512 bf16
+  const int q0 = blockIdx.z * kAttQ;
+  if (q0 >= T) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, tig = lane & 3;
+  const size_t row_stride = 3 * kDim;
+  const __nv_bfloat16* base = qkv + (size_t)t0 * row_stride + head * kHeadDim;
+
+  // Q fragments (A operand) for rows r_lo = q0 + 16*warp + g and r_lo + 8; rows past the clip read row T-1 (never stored)
+  const int r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8;
+  const __nv_bfloat16* q_lo = base + (size_t)min(r_lo, T - 1) * row_stride;
+  const __nv_bfloat16* q_hi = base + (size_t)min(r_hi, T - 1) * row_stride;
+  uint32_t qa[2][4];
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    qa[ks][0] = *reinterpret_cast<const uint32_t*>(q_lo + 16 * ks + 2 * tig);
+    qa[ks][1] = *reinterpret_cast<const uint32_t*>(q_hi + 16 * ks + 2 * tig);
+    qa[ks][2] = *reinterpret_cast<const uint32_t*>(q_lo + 16 * ks + 2 * tig + 8);
+    qa[ks][3] = *reinterpret_cast<const uint32_t*>(q_hi + 16 * ks + 2 * tig + 8);
   }
-  __syncthreads();
-  const float scale = 0.17677669529663687f;  // 1/sqrt(32)
-  for (int qi = threadIdx.x; qi < T; qi += blockDim.x) {
-    float q[kHeadDim];
-    {
-      const uint4* row = reinterpret_cast<const uint4*>(qkv + (size_t)(t0 + qi) * (3 * kDim) + head * kHeadDim);
+  const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  float o[4][4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 u = row[c];
-        const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+  for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(p[e]);
-          q[c * 8 + 2 * e] = f.x * scale;
-          q[c * 8 + 2 * e + 1] = f.y * scale;
-        }
+    for (int i = 0; i < 4; ++i) o[j][i] = 0.f;
+
+  for (int k0 = 0; k0 < T; k0 += kAttKeys) {
+    __syncthreads();  // previous block fully consumed
+    for (int i = threadIdx.x; i < kAttKeys * 4; i += 128) {
+      const int key = i >> 2, c = i & 3;
+      uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
+      if (k0 + key < T) {
+        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)(k0 + key) * row_stride);
+        kq = src[kDim / 8 + c];
+        vq = src[2 * kDim / 8 + c];
+      }
+      *reinterpret_cast<uint4*>(Ks + key * kAttKPitch + c * 8) = kq;
+      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vq);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) Vt[(c * 8 + e) * kAttVPitch + key] = ve[e];
+    }
+    __syncthreads();
+
+    // S = Q K^T for 64 keys: 8 n-tiles of 8 keys
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+      const __nv_bfloat16* kr = Ks + (8 * j + g) * kAttKPitch + 2 * tig;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma_16816(s[j], qa[ks], *reinterpret_cast<const uint32_t*>(kr + 16 * ks), *reinterpret_cast<const uint32_t*>(kr + 16 * ks + 8));
+    }
+    // scale to log2 domain, mask keys past the clip, block row maxima
+    float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key = k0 + 8 * j + 2 * tig;
+      const bool v0 = key < T, v1 = key + 1 < T;
+      s[j][0] = v0 ? s[j][0] * sl2 : -INFINITY;
+      s[j][1] = v1 ? s[j][1] * sl2 : -INFINITY;
+      s[j][2] = v0 ? s[j][2] * sl2 : -INFINITY;
+      s[j][3] = v1 ? s[j][3] * sl2 : -INFINITY;
+      mx_lo = fmaxf(mx_lo, fmaxf(s[j][0], s[j][1]));
+      mx_hi = fmaxf(mx_hi, fmaxf(s[j][2], s[j][3]));
+    }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);  // finite: key k0 is always valid
+    const float c_lo = exp2f(m_lo - mn_lo), c_hi = exp2f(m_hi - mn_hi);
+    m_lo = mn_lo;
+    m_hi = mn_hi;
+    l_lo *= c_lo;
+    l_hi *= c_hi;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      o[j][0] *= c_lo; o[j][1] *= c_lo; o[j][2] *= c_hi; o[j][3] *= c_hi;
+    }
+    // P = exp2(S - m); O += P V  (P re-used straight from the accumulator registers as the A operand)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t pa[4];
+      float p[2][4];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int j = 2 * kk + h;
+        p[h][0] = exp2f(s[j][0] - m_lo);
+        p[h][1] = exp2f(s[j][1] - m_lo);
+        p[h][2] = exp2f(s[j][2] - m_hi);
+        p[h][3] = exp2f(s[j][3] - m_hi);
+        l_lo += p[h][0] + p[h][1];
+        l_hi += p[h][2] + p[h][3];
+      }
+      pa[0] = pack_bf16x2(p[0][0], p[0][1]);
+      pa[1] = pack_bf16x2(p[0][2], p[0][3]);
+      pa[2] = pack_bf16x2(p[1][0], p[1][1]);
+      pa[3] = pack_bf16x2(p[1][2], p[1][3]);
+#pragma unroll
+      for (int jd = 0; jd < 4; ++jd) {
+        const __nv_bfloat16* vr = Vt + (8 * jd + g) * kAttVPitch + 16 * kk + 2 * tig;
+        mma_16816(o[jd], pa, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
       }
     }
-    float m = -INFINITY, l = 0.f;
-    float o[kHeadDim];
+  }
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
+  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
+  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
+  const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
+  __nv_bfloat16* o_lo = out + (size_t)(t0 + r_lo) * kDim + head * kHeadDim + 2 * tig;
+  __nv_bfloat16* o_hi = out + (size_t)(t0 + r_hi) * kDim + head * kHeadDim + 2 * tig;
 #pragma unroll
-    for (int d = 0; d < kHeadDim; ++d) o[d] = 0.f;
-    for (int j = 0; j < T; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 u = ks[j * 4 + c];
-        const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(p[e]);
-          s += q[c * 8 + 2 * e] * f.x + q[c * 8 + 2 * e + 1] * f.y;
-        }
-      }
-      const float m_new = fmaxf(m, s);
-      const float corr = __expf(m - m_new);
-      const float pj = __expf(s - m_new);
-      l = l * corr + pj;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const uint4 u = vs[j * 4 + c];
-        const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(p[e]);
-          o[c * 8 + 2 * e] = o[c * 8 + 2 * e] * corr + pj * f.x;
-          o[c * 8 + 2 * e + 1] = o[c * 8 + 2 * e + 1] * corr + pj * f.y;
-        }
-      }
-      m = m_new;
-    }
-    const float inv = 1.0f / l;
-    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(t0 + qi) * kDim + head * kHeadDim);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      uint4 u;
-      u.x = pack_bf16x2(o[c * 8 + 0] * inv, o[c * 8 + 1] * inv);
-      u.y = pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
-      u.z = pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv);
-      u.w = pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
-      dst[c] = u;
-    }
+  for (int jd = 0; jd < 4; ++jd) {
+    if (r_lo < T) *reinterpret_cast<uint32_t*>(o_lo + 8 * jd) = pack_bf16x2(o[jd][0] * i_lo, o[jd][1] * i_lo);
+    if (r_hi < T) *reinterpret_cast<uint32_t*>(o_hi + 8 * jd) = pack_bf16x2(o[jd][2] * i_hi, o[jd][3] * i_hi);
   }
 }
 
@@ -194,7 +257,7 @@ attention_clip_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restri
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 temporal_pool_kernel(const float* __restrict__ x, const float* __restrict__ logits, const int* __restrict__ cu,
-                     float* __restrict__ pooled /*[clips][768]*/) {
+                     float* __restrict__ pooled /*[clips][768]*/, __nv_bfloat16* __restrict__ pooled_bf /*same, bf16*/) {
   const int clip = blockIdx.x, c = threadIdx.x;
   const int t0 = cu[clip], T = cu[clip + 1] - t0;
   float sum = 0.f, mx = -INFINITY, m = -INFINITY, l = 0.f, ws = 0.f;
@@ -211,9 +274,14 @@ temporal_pool_kernel(const float* __restrict__ x, const float* __restrict__ logi
     m = m_new;
   }
   float* o = pooled + (size_t)clip * (3 * kDim);
-  o[c] = sum / (float)T;
+  __nv_bfloat16* ob = pooled_bf + (size_t)clip * (3 * kDim);
+  const float avg = sum / (float)T, wsum = ws / l;
+  o[c] = avg;
   o[kDim + c] = mx;
-  o[2 * kDim + c] = ws / l;
+  o[2 * kDim + c] = wsum;
+  ob[c] = __float2bfloat16(avg);
+  ob[kDim + c] = __float2bfloat16(mx);
+  ob[2 * kDim + c] = __float2bfloat16(wsum);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -85,6 +85,14 @@ struct Profiler {
 Profiler g_prof;
 const int kTemporalKernels[4] = {3, 5, 7, 11};
 
+// conv2 reads conv1's output in space-to-depth form [frame][16][16][(sh*2+sw)*32 + c] (a cell = 2x2 pixels).
+// A 3x3/stride-2 tap (kh, kw) lives in cell offset d = {-1,0,0}[k], sub-position s = {1,0,1}[k]. K blocks are
+// 64 channels (= two horizontally adjacent sub-pixels, one full 128-byte TMA row): {channel half, dw, dh}.
+// Sub-pixels a block does not need (dw = -1 only uses sw = 1) get zero weights, so K = 6 * 64 = 384 (288 real).
+struct Conv2KBlock { int c_half, dw, dh; };
+const Conv2KBlock kConv2KBlocks[6] = {{1, 0, -1}, {0, 0, 0}, {1, 0, 0}, {1, -1, -1}, {0, -1, 0}, {1, -1, 0}};
+inline int conv2_tap_index(int d, int sub) { return d == -1 ? (sub == 1 ? 0 : -1) : (sub == 0 ? 1 : 2); }
+
 struct AttnBlockWeights {
   float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
   __nv_bfloat16 *wqkv, *wo, *w1, *w2;
@@ -119,6 +127,10 @@ struct vfp_weights {
   float* bpool = nullptr;
   CUtensorMap tm_pool;
   float *w0t = nullptr, *b0 = nullptr, *w3t = nullptr, *b3 = nullptr;
+  // head on tensor cores (embedding_dim <= 256 and a multiple of 32): bf16 K-major copies of both layers
+  bool head_on_tensor_cores = false;
+  __nv_bfloat16 *w0_bf = nullptr, *w3_bf = nullptr;
+  CUtensorMap tm_head0, tm_head3;
 };
 
 namespace {
@@ -211,13 +223,22 @@ int prep_f32(vfp_weights* w, const float* src, size_t n, float** dev) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// forward workspace
+// forward workspace. Two regions with different granularity:
+//   * the TOKEN region holds one "token pass" (up to all clips of the call): 8.5 KB per frame/token. The token
+//     GEMMs, LayerNorm, attention, pooling and the head each run ONCE per token pass, so their launches are large;
+//   * the CONV region holds the activations of one "conv pass" (kConvPassFrames frames, 112 KB per frame): the
+//     frame encoder walks the token pass in such slices and only leaves the 512 B/frame pooled features behind.
 // ---------------------------------------------------------------------------------------------
-struct ForwardWs {
-  size_t cu, tok_pos, tok_len, c1, c2, c3, feat, xa, xb, xn, qkv, att, h, logits, xbf, pooled, total;
+constexpr int64_t kConvPassFrames = 16384;
+
+struct TokenWs {
+  size_t cu, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, h, logits, xbf, pooled, pooled_bf, head_h, total;
 };
-ForwardWs forward_ws_layout(int64_t F, int64_t C) {
-  ForwardWs L{};
+struct ConvWs {
+  size_t c1, c2, c3, total;
+};
+TokenWs token_ws_layout(int64_t F, int64_t C) {
+  TokenWs L{};
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
@@ -227,9 +248,6 @@ ForwardWs forward_ws_layout(int64_t F, int64_t C) {
   L.cu = take((size_t)(C + 1) * 4);
   L.tok_pos = take((size_t)F * 4);
   L.tok_len = take((size_t)F * 4);
-  L.c1 = take((size_t)F * 32 * 32 * 32 * 2);
-  L.c2 = take((size_t)F * 16 * 16 * 64 * 2);
-  L.c3 = take((size_t)F * 8 * 8 * 128 * 2);
   L.feat = take((size_t)F * 256 * 2);
   L.xa = take((size_t)F * kDim * 4);
   L.xb = take((size_t)F * kDim * 4);
@@ -240,8 +258,27 @@ ForwardWs forward_ws_layout(int64_t F, int64_t C) {
   L.logits = take((size_t)F * kDim * 4);
   L.xbf = take((size_t)F * kDim * 2);
   L.pooled = take((size_t)C * 3 * kDim * 4);
+  L.pooled_bf = take((size_t)C * 3 * kDim * 2);
+  L.head_h = take((size_t)C * kDim * 2);
   L.total = off;
   return L;
+}
+ConvWs conv_ws_layout(int64_t F) {
+  ConvWs L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = align_up(off + bytes, 1024);
+    return o;
+  };
+  L.c1 = take((size_t)F * 32 * 32 * 32 * 2);
+  L.c2 = take((size_t)F * 16 * 16 * 64 * 2);
+  L.c3 = take((size_t)F * 8 * 8 * 128 * 2);
+  L.total = off;
+  return L;
+}
+size_t forward_ws_total(int64_t F, int64_t C) {
+  return token_ws_layout(F, C).total + conv_ws_layout(std::min<int64_t>(F, kConvPassFrames)).total;
 }
 
 constexpr int kMaxClipFrames = 1024;
@@ -343,7 +380,25 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
     if (upload(w, pack, &w->c1_wpack) || upload(w, bias, &w->c1_bias)) return bail("");
   }
   // ---- conv2..4 ----
-  if (prep_conv3x3(w, t, 3, 32, 64, &w->c2_w, &w->c2_b, &err)) return bail(err);
+  {  // conv2: K laid out to match kConv2KBlocks (see there)
+    const float* cw = t.get(enc + "3.weight", 64 * 32 * 9, &err);
+    const float* cb = cw ? t.get(enc + "3.bias", 64, &err) : nullptr;
+    BnFold bn;
+    if (!cb || !load_bn(t, enc + "4", 64, &bn, &err)) return bail(err);
+    std::vector<float> wf((size_t)64 * 384, 0.0f), bf(64);
+    for (int co = 0; co < 64; ++co) {
+      for (int kb = 0; kb < 6; ++kb)
+        for (int j = 0; j < 2; ++j) {
+          const int block = 2 * kConv2KBlocks[kb].c_half + j, sh = block >> 1, sw = block & 1;
+          const int kh = conv2_tap_index(kConv2KBlocks[kb].dh, sh), kw = conv2_tap_index(kConv2KBlocks[kb].dw, sw);
+          if (kh < 0 || kw < 0) continue;
+          for (int c = 0; c < 32; ++c)
+            wf[(size_t)co * 384 + kb * 64 + j * 32 + c] = cw[((co * 32 + c) * 3 + kh) * 3 + kw] * bn.scale[co];
+        }
+      bf[co] = cb[co] * bn.scale[co] + bn.shift[co];
+    }
+    if (upload(w, to_bf16(wf), &w->c2_w) || upload(w, bf, &w->c2_b)) return bail("");
+  }
   if (prep_conv3x3(w, t, 6, 64, 128, &w->c3_w, &w->c3_b, &err)) return bail(err);
   if (prep_conv3x3(w, t, 9, 128, 256, &w->c4_w, &w->c4_b, &err)) return bail(err);
 
@@ -446,8 +501,16 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
         upload(w, w0t, &w->w0t) || prep_f32(w, b0, kDim, &w->b0) || upload(w, w3t, &w->w3t) ||
         prep_f32(w, b3, (size_t)D, &w->b3))
       return bail("");
+    if (D <= 256 && D % 32 == 0) {
+      if (prep_dense_bf16(w, w0, (size_t)kDim * 3 * kDim, &w->w0_bf) || prep_dense_bf16(w, w3, (size_t)D * kDim, &w->w3_bf))
+        return bail("");
+      if (make_tmap_rows_bf16(&w->tm_head0, w->w0_bf, kDim, 3 * kDim, 3 * kDim, 256, 64) ||
+          make_tmap_rows_bf16(&w->tm_head3, w->w3_bf, (uint64_t)D, kDim, kDim, 256, 64))
+        return bail("tensor map encode failed (head)");
+      w->head_on_tensor_cores = true;
+    }
   }
-  if (make_tmap_rows_bf16(&w->tm_c2, w->c2_w, 64, 288, 288, 64, 32) ||
+  if (make_tmap_rows_bf16(&w->tm_c2, w->c2_w, 64, 384, 384, 64, 64) ||
       make_tmap_rows_bf16(&w->tm_c3, w->c3_w, 128, 576, 576, 128, 64) ||
       make_tmap_rows_bf16(&w->tm_c4, w->c4_w, 256, 1152, 1152, 256, 64) ||
       make_tmap_rows_bf16(&w->tm_tok, w->wtok, kDim, 256, 256, 256, 64) ||
@@ -461,27 +524,79 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
 size_t vfp_forward_workspace_bytes(int64_t frames_per_pass, int64_t clips_per_pass) {
   if (frames_per_pass <= 0) return 0;
   if (clips_per_pass <= 0 || clips_per_pass > frames_per_pass) clips_per_pass = frames_per_pass;
-  return forward_ws_layout(frames_per_pass, clips_per_pass).total;
+  return forward_ws_total(frames_per_pass, clips_per_pass);
 }
 
 }  // extern "C"
 
 namespace {
 
-// One pass: clips [c0, c1) = frames [f0, f0 + F) of the packed input.
+// Frame encoder over frames [f0, f0 + F) of the packed input -> feat[f_rel0 + i] (bf16 [frames][256]).
+int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dtype, int64_t F, __nv_bfloat16* feat_out,
+                       uint8_t* conv_ws, cudaStream_t st) {
+  const ConvWs L = conv_ws_layout(F);
+  __nv_bfloat16* c1a = reinterpret_cast<__nv_bfloat16*>(conv_ws + L.c1);
+  __nv_bfloat16* c2a = reinterpret_cast<__nv_bfloat16*>(conv_ws + L.c2);
+  __nv_bfloat16* c3a = reinterpret_cast<__nv_bfloat16*>(conv_ws + L.c3);
+  g_prof.launches += 4;
+  {
+    const long long grid = std::min<long long>(F, (long long)device_sm_count() * 8);
+    conv1_stem_kernel<<<(unsigned)grid, kC1Threads, 0, st>>>(frames, frame_dtype, F, w->c1_wpack, w->c1_bias, c1a);
+    g_prof.mark(kStConv1, st);
+  }
+  CUtensorMap ta;
+  {  // conv2: c1 is stored space-to-depth [frame][16][16][4*32] -> dense 2x2/stride-1 taps; tile = 8 rows x 16 cols
+    if (make_tmap_nhwc_bf16(&ta, c1a, F, 16, 16, 128, 64, 16, 8, 1, 1)) return fail("tensor map encode failed (conv2)");
+    GemmShape s{};
+    s.m_tiles = (int)(2 * F); s.n_tiles = 1; s.k_blocks = 6; s.group_m = 16; s.a_conv = 1;
+    s.tiles_per_frame = 2; s.frames_per_tile = 1; s.tile_out_rows = 8; s.h_mul = 1;
+    for (int kb = 0; kb < 6; ++kb) {
+      s.tap_c_blk[kb] = (signed char)kConv2KBlocks[kb].c_half;
+      s.tap_w[kb] = (signed char)kConv2KBlocks[kb].dw;
+      s.tap_h[kb] = (signed char)kConv2KBlocks[kb].dh;
+    }
+    EpiBiasAct::Params ep{};
+    ep.bias = w->c2_b; ep.out_bf16 = c2a; ep.ld_out = 64; ep.M = (int)(F * 256); ep.N = 64; ep.act = 1;
+    VFP_CUDA((launch_gemm<64, 64, 8, EpiBiasAct>(ta, w->tm_c2, s, ep, st)));
+    g_prof.mark(kStConv2, st);
+  }
+  {  // conv3: 16x16x64 -> 8x8x128 through a stride-2 box, tile = 2 frames
+    if (make_tmap_nhwc_bf16(&ta, c2a, F, 16, 16, 64, 64, 8, 8, 2, 2)) return fail("tensor map encode failed (conv3)");
+    GemmShape s{};
+    s.m_tiles = (int)((F + 1) / 2); s.n_tiles = 1; s.k_blocks = 9; s.group_m = 16; s.a_conv = 1;
+    s.tiles_per_frame = 1; s.frames_per_tile = 2; s.tile_out_rows = 8;
+    conv_taps_strided(&s, 1);
+    EpiBiasAct::Params ep{};
+    ep.bias = w->c3_b; ep.out_bf16 = c3a; ep.ld_out = 128; ep.M = (int)(F * 64); ep.N = 128; ep.act = 1;
+    VFP_CUDA((launch_gemm<128, 64, 6, EpiBiasAct>(ta, w->tm_c3, s, ep, st)));
+    g_prof.mark(kStConv3, st);
+  }
+  {  // conv4: 8x8x128 -> 4x4x256 + ReLU + global average pool, tile = 8 frames
+    if (make_tmap_nhwc_bf16(&ta, c3a, F, 8, 8, 128, 64, 4, 4, 8, 2)) return fail("tensor map encode failed (conv4)");
+    GemmShape s{};
+    s.m_tiles = (int)((F + 7) / 8); s.n_tiles = 1; s.k_blocks = 18; s.group_m = 16; s.a_conv = 1;
+    s.tiles_per_frame = 1; s.frames_per_tile = 8; s.tile_out_rows = 4;
+    conv_taps_strided(&s, 2);
+    EpiConvPool16::Params ep{};
+    ep.bias = w->c4_b; ep.out_bf16 = feat_out; ep.frames = (int)F; ep.N = 256;
+    VFP_CUDA((launch_gemm<256, 64, 4, EpiConvPool16>(ta, w->tm_c4, s, ep, st)));
+    g_prof.mark(kStConv4, st);
+  }
+  return 0;
+}
+
+// One token pass: clips [c0, c1) = frames [f0, f0 + F) of the packed input.
 int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dtype, size_t frame_bytes,
                  const int32_t* cu_host, int c0, int c1, float* emb_out, float* features_out, uint8_t* ws,
                  cudaStream_t st) {
   const int C = c1 - c0;
   const int64_t f0 = cu_host[c0];
   const int64_t F = cu_host[c1] - f0;
-  const ForwardWs L = forward_ws_layout(F, C);
+  const TokenWs L = token_ws_layout(F, C);
+  uint8_t* conv_ws = ws + L.total;
   int* d_cu = reinterpret_cast<int*>(ws + L.cu);
   int* tok_pos = reinterpret_cast<int*>(ws + L.tok_pos);
   int* tok_len = reinterpret_cast<int*>(ws + L.tok_len);
-  __nv_bfloat16* c1a = reinterpret_cast<__nv_bfloat16*>(ws + L.c1);
-  __nv_bfloat16* c2a = reinterpret_cast<__nv_bfloat16*>(ws + L.c2);
-  __nv_bfloat16* c3a = reinterpret_cast<__nv_bfloat16*>(ws + L.c3);
   __nv_bfloat16* feat = reinterpret_cast<__nv_bfloat16*>(ws + L.feat);
   float* xa = reinterpret_cast<float*>(ws + L.xa);
   float* xb = reinterpret_cast<float*>(ws + L.xb);
@@ -492,6 +607,8 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   float* logits = reinterpret_cast<float*>(ws + L.logits);
   __nv_bfloat16* xbf = reinterpret_cast<__nv_bfloat16*>(ws + L.xbf);
   float* pooled = reinterpret_cast<float*>(ws + L.pooled);
+  __nv_bfloat16* pooled_bf = reinterpret_cast<__nv_bfloat16*>(ws + L.pooled_bf);
+  __nv_bfloat16* head_h = reinterpret_cast<__nv_bfloat16*>(ws + L.head_h);
 
   // clip prefix sums relative to this pass
   std::vector<int32_t> cu_rel(C + 1);
@@ -499,63 +616,30 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   for (int i = 0; i <= C; ++i) cu_rel[i] = (int32_t)(cu_host[c0 + i] - f0);
   for (int i = 0; i < C; ++i) max_T = std::max(max_T, cu_rel[i + 1] - cu_rel[i]);
   g_prof.mark(-1, st);
-  g_prof.launches += 12 + 7 * (unsigned long long)w->n_attn;
+  g_prof.launches += 8 + 7 * (unsigned long long)w->n_attn;
   VFP_CUDA(cudaMemcpyAsync(d_cu, cu_rel.data(), (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, st));
   // cu_rel is pageable: the copy is staged before the call returns, so the vector may die with this scope.
   token_map_kernel<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(d_cu, C, (int)F, tok_pos, tok_len);
   g_prof.mark(kStMisc, st);
 
-  // ---- frame encoder ----
-  const int sms = device_sm_count();
-  {
-    const long long grid = std::min<long long>(F, (long long)sms * 8);
-    conv1_stem_kernel<<<(unsigned)grid, kC1Threads, 0, st>>>(frames_base + (size_t)f0 * frame_bytes, frame_dtype, F,
-                                                            w->c1_wpack, w->c1_bias, c1a);
-    g_prof.mark(kStConv1, st);
-  }
-  CUtensorMap ta;
-  {  // conv2: 32x32x32 -> 16x16x64, tile = 8 output rows x 16 cols of one frame
-    if (make_tmap_conv_s2_bf16(&ta, c1a, F, 32, 32, 32, 32, 16, 8, 1)) return fail("tensor map encode failed (conv2)");
-    GemmShape s{};
-    s.m_tiles = (int)(2 * F); s.n_tiles = 1; s.k_blocks = 9; s.group_m = 16; s.a_conv = 1;
-    s.tiles_per_frame = 2; s.frames_per_tile = 1; s.tile_out_rows = 8; s.cblocks_per_tap = 1;
-    EpiBiasAct::Params ep{};
-    ep.bias = w->c2_b; ep.out_bf16 = c2a; ep.ld_out = 64; ep.M = (int)(F * 256); ep.N = 64; ep.act = 1;
-    VFP_CUDA((launch_gemm<64, 32, 8, EpiBiasAct>(ta, w->tm_c2, s, ep, st)));
-    g_prof.mark(kStConv2, st);
-  }
-  {  // conv3: 16x16x64 -> 8x8x128, tile = 2 frames
-    if (make_tmap_conv_s2_bf16(&ta, c2a, F, 16, 16, 64, 64, 8, 8, 2)) return fail("tensor map encode failed (conv3)");
-    GemmShape s{};
-    s.m_tiles = (int)((F + 1) / 2); s.n_tiles = 1; s.k_blocks = 9; s.group_m = 16; s.a_conv = 1;
-    s.tiles_per_frame = 1; s.frames_per_tile = 2; s.tile_out_rows = 8; s.cblocks_per_tap = 1;
-    EpiBiasAct::Params ep{};
-    ep.bias = w->c3_b; ep.out_bf16 = c3a; ep.ld_out = 128; ep.M = (int)(F * 64); ep.N = 128; ep.act = 1;
-    VFP_CUDA((launch_gemm<128, 64, 6, EpiBiasAct>(ta, w->tm_c3, s, ep, st)));
-    g_prof.mark(kStConv3, st);
-  }
-  {  // conv4: 8x8x128 -> 4x4x256 + ReLU + global average pool, tile = 8 frames
-    if (make_tmap_conv_s2_bf16(&ta, c3a, F, 8, 8, 128, 64, 4, 4, 8)) return fail("tensor map encode failed (conv4)");
-    GemmShape s{};
-    s.m_tiles = (int)((F + 7) / 8); s.n_tiles = 1; s.k_blocks = 18; s.group_m = 16; s.a_conv = 1;
-    s.tiles_per_frame = 1; s.frames_per_tile = 8; s.tile_out_rows = 4; s.cblocks_per_tap = 2;
-    EpiConvPool16::Params ep{};
-    ep.bias = w->c4_b; ep.out_bf16 = feat; ep.frames = (int)F; ep.N = 256;
-    VFP_CUDA((launch_gemm<256, 64, 4, EpiConvPool16>(ta, w->tm_c4, s, ep, st)));
-    g_prof.mark(kStConv4, st);
+  // ---- frame encoder, one conv pass at a time (frames are independent: slices ignore clip boundaries) ----
+  for (int64_t s0 = 0; s0 < F; s0 += kConvPassFrames) {
+    const int64_t n = std::min<int64_t>(kConvPassFrames, F - s0);
+    if (int rc = encode_frames_pass(w, frames_base + (size_t)(f0 + s0) * frame_bytes, frame_dtype, n, feat + s0 * 256, conv_ws, st))
+      return rc;
   }
   // ---- token embedding: x = Wtok feat + btok + pe[pos] ----
-  auto token_gemm = [&](const __nv_bfloat16* A, int K, const CUtensorMap& tb, int N, const EpiBiasAct::Params& ep) -> int {
+  auto token_gemm = [&](const __nv_bfloat16* A, int64_t M, int K, const CUtensorMap& tb, int N, const EpiBiasAct::Params& ep) -> int {
     CUtensorMap tma;
-    if (make_tmap_rows_bf16(&tma, A, (uint64_t)F, (uint64_t)K, (uint64_t)K, 128, 64)) return fail("tensor map encode failed (tokens)");
-    GemmShape s = plain_shape(F, N, K, 256, 64, 32);
+    if (make_tmap_rows_bf16(&tma, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 64)) return fail("tensor map encode failed (tokens)");
+    GemmShape s = plain_shape(M, N, K, 256, 64, 32);
     VFP_CUDA((launch_gemm<256, 64, 4, EpiBiasAct>(tma, tb, s, ep, st)));
     return 0;
   };
   {
     EpiBiasAct::Params ep{};
     ep.bias = w->btok; ep.pe = w->pe; ep.token_pos = tok_pos; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
-    if (token_gemm(feat, 256, w->tm_tok, kDim, ep)) return 1;
+    if (token_gemm(feat, F, 256, w->tm_tok, kDim, ep)) return 1;
     g_prof.mark(kStTokEmbed, st);
   }
   // ---- multi-scale temporal convolutions (residual) ----
@@ -567,12 +651,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   }
   // ---- attention blocks ----
   const unsigned ln_grid = (unsigned)((F * 32 + 255) / 256);
-  const size_t att_smem = (size_t)max_T * 128;
-  static bool att_configured = false;
-  if (!att_configured) {
-    VFP_CUDA(cudaFuncSetAttribute(attention_clip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxClipFrames * 128));
-    att_configured = true;
-  }
+  const dim3 att_grid((unsigned)C, kHeads, (unsigned)((max_T + kAttQ - 1) / kAttQ));
   for (int b = 0; b < w->n_attn; ++b) {
     const AttnBlockWeights& a = w->attn[b];
     layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, a.ln1_w, a.ln1_b, xn, (int)F);
@@ -580,15 +659,15 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     {
       EpiBiasAct::Params ep{};
       ep.bias = a.bqkv; ep.out_bf16 = qkv; ep.ld_out = 3 * kDim; ep.M = (int)F; ep.N = 3 * kDim;
-      if (token_gemm(xn, kDim, a.tm_qkv, 3 * kDim, ep)) return 1;
+      if (token_gemm(xn, F, kDim, a.tm_qkv, 3 * kDim, ep)) return 1;
       g_prof.mark(kStQkv, st);
     }
-    attention_clip_kernel<<<dim3((unsigned)C, kHeads), 128, att_smem, st>>>(qkv, d_cu, att);
+    attention_mma_kernel<<<att_grid, 128, 0, st>>>(qkv, d_cu, att);
     g_prof.mark(kStAttention, st);
     {
       EpiBiasAct::Params ep{};
       ep.bias = a.bo; ep.residual = xa; ep.ld_res = kDim; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
-      if (token_gemm(att, kDim, a.tm_o, kDim, ep)) return 1;
+      if (token_gemm(att, F, kDim, a.tm_o, kDim, ep)) return 1;
       g_prof.mark(kStOutProj, st);
     }
     layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, a.ln2_w, a.ln2_b, xn, (int)F);
@@ -596,13 +675,13 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     {
       EpiBiasAct::Params ep{};
       ep.bias = a.b1; ep.act = 2; ep.out_bf16 = hbuf; ep.ld_out = 4 * kDim; ep.M = (int)F; ep.N = 4 * kDim;
-      if (token_gemm(xn, kDim, a.tm_w1, 4 * kDim, ep)) return 1;
+      if (token_gemm(xn, F, kDim, a.tm_w1, 4 * kDim, ep)) return 1;
       g_prof.mark(kStMlp1, st);
     }
     {
       EpiBiasAct::Params ep{};
       ep.bias = a.b2; ep.residual = xa; ep.ld_res = kDim; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
-      if (token_gemm(hbuf, 4 * kDim, a.tm_w2, kDim, ep)) return 1;
+      if (token_gemm(hbuf, F, 4 * kDim, a.tm_w2, kDim, ep)) return 1;
       g_prof.mark(kStMlp2, st);
     }
   }
@@ -613,13 +692,27 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   {
     EpiBiasAct::Params ep{};
     ep.bias = w->bpool; ep.act = 1; ep.out_f32 = logits; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
-    if (token_gemm(xbf, kDim, w->tm_pool, kDim, ep)) return 1;
+    if (token_gemm(xbf, F, kDim, w->tm_pool, kDim, ep)) return 1;
     g_prof.mark(kStPoolGemm, st);
   }
-  temporal_pool_kernel<<<(unsigned)C, 256, 0, st>>>(xa, logits, d_cu, pooled);
+  temporal_pool_kernel<<<(unsigned)C, 256, 0, st>>>(xa, logits, d_cu, pooled, pooled_bf);
   g_prof.mark(kStPool, st);
-  final_projection_kernel<8><<<(unsigned)((C + 7) / 8), 256, 0, st>>>(pooled, w->w0t, w->b0, w->w3t, w->b3, w->embedding_dim,
-                                                                   C, emb_out + (size_t)c0 * w->embedding_dim);
+  float* emb_dst = emb_out + (size_t)c0 * w->embedding_dim;
+  if (w->head_on_tensor_cores) {
+    // final_projection as two tcgen05 GEMMs: [C,768]x[768,256] + ReLU, then [C,256]x[256,D] + bias + L2 normalise
+    EpiBiasAct::Params ep{};
+    ep.bias = w->b0; ep.act = 1; ep.out_bf16 = head_h; ep.ld_out = kDim; ep.M = C; ep.N = kDim;
+    if (token_gemm(pooled_bf, C, 3 * kDim, w->tm_head0, kDim, ep)) return 1;
+    CUtensorMap tma;
+    if (make_tmap_rows_bf16(&tma, head_h, (uint64_t)C, kDim, kDim, 128, 64)) return fail("tensor map encode failed (head)");
+    GemmShape s = plain_shape(C, w->embedding_dim, kDim, 256, 64, 32);
+    EpiBiasL2Norm::Params en{};
+    en.bias = w->b3; en.out_f32 = emb_dst; en.M = C; en.N = w->embedding_dim;
+    VFP_CUDA((launch_gemm<256, 64, 4, EpiBiasL2Norm>(tma, w->tm_head3, s, en, st)));
+  } else {
+    final_projection_kernel<8><<<(unsigned)((C + 7) / 8), 256, 0, st>>>(pooled, w->w0t, w->b0, w->w3t, w->b3, w->embedding_dim,
+                                                                     C, emb_dst);
+  }
   g_prof.mark(kStFinal, st);
   if (g_prof.marks.size() > 4096) g_prof.drain();
   VFP_CUDA(cudaGetLastError());
@@ -650,12 +743,12 @@ int vfp_forward(const vfp_weights* w, const void* frames, int frame_dtype, const
   int64_t lo = 0, hi = cu[n_clips];
   while (lo < hi) {
     const int64_t mid = (lo + hi + 1) / 2;
-    if (forward_ws_layout(mid, std::min<int64_t>(mid, n_clips)).total <= workspace_bytes) lo = mid; else hi = mid - 1;
+    if (forward_ws_total(mid, std::min<int64_t>(mid, n_clips)) <= workspace_bytes) lo = mid; else hi = mid - 1;
   }
   const int64_t pass_frames = lo;
   if (pass_frames < max_T)
     return fail("vfp_forward: workspace of " + std::to_string(workspace_bytes) + " bytes cannot hold the longest clip (" +
-                std::to_string(max_T) + " frames need " + std::to_string(forward_ws_layout(max_T, 1).total) + ")");
+                std::to_string(max_T) + " frames need " + std::to_string(forward_ws_total(max_T, 1)) + ")");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int c0 = 0;
   while (c0 < n_clips) {

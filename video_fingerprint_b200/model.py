@@ -102,7 +102,7 @@ class VideoFingerprintAttention(nn.Module):
         )
         self.temperature = nn.Parameter(torch.ones(1) * 0.07)
         self.embedding_dim = embedding_dim
-        self.frames_per_pass = 8192  # frames pushed through the network per internal pass (workspace ~ 124 KB/frame)
+        self.frames_per_pass = 1 << 20  # frames per token pass (workspace: 8.5 KB/frame + 1.8 GB for the conv pass)
         self._native_weights: Optional[int] = None
         self._native_key: Optional[tuple] = None
         self._workspace: Optional[torch.Tensor] = None
