@@ -94,8 +94,11 @@ int vfp_join_threshold(const float* q, const float* db, int64_t n_q, int64_t n_d
 
 /* Exact flat inner-product top-k (the arithmetic of faiss.IndexFlatIP.search): for every query row the k
  * largest <q_i, db_j> in fp32, sorted by (score descending, index ascending). out_s (n_q, k) fp32,
- * out_idx (n_q, k) int64, device memory. k <= 32. `flags_out` (device, 1 x uint64) counts query rows whose
- * exactness could not be proven by the bf16 screen bound and were recomputed by the fp32 fallback. */
+ * out_idx (n_q, k) int64, device memory. k <= 32, dim == 256. The tensor-core screen keeps the 64 best bf16 scores
+ * per query, which are re-scored in fp32; `flags_out` (device, 2 x uint64): [0] = query rows whose exactness could
+ * not be proven from the screen bound (`screen_margin`, as for the join) and were recomputed by the exact fp32
+ * scan, [1] != 0 = that fallback overflowed (more than 8192 such rows or more than 512 tied candidates for one
+ * row) and the result must be discarded. */
 size_t vfp_topk_workspace_bytes(int64_t n_q, int64_t n_db, int k);
 int vfp_topk_ip(const float* q, const float* db, int64_t n_q, int64_t n_db, int dim, int k,
                 float screen_margin, float* out_s, int64_t* out_idx, uint64_t* flags_out, void* workspace,

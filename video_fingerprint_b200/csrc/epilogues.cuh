@@ -12,10 +12,19 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
+// Defaults shared by the epilogues: one sweep over the accumulator, no state across tiles, no extra smem.
+struct EpiDefaults {
+  static constexpr int kPasses = 1;
+  static constexpr int kColumnSplit = 2;
+  static constexpr int kExtraSmemBytes = 0;
+  template <class P> __device__ __forceinline__ void item_begin(const P&, int, int, int, uint8_t*) {}
+  template <class P> __device__ __forceinline__ void item_end(const P&, int, int, int, uint8_t*) {}
+};
+
 // -------------------------------------------------------------------------------------------
 // y = act(acc + bias [+ pe[pos[row]]]) [+ residual]  -> fp32 and/or bf16 row-major outputs
 // -------------------------------------------------------------------------------------------
-struct EpiBiasAct {
+struct EpiBiasAct : EpiDefaults {
   struct Params {
     const float* bias;       // [N] or null
     const float* residual;   // [M][ld_res] fp32 or null (added after the activation)
@@ -27,8 +36,6 @@ struct EpiBiasAct {
     int M, N;
     int act;  // 0 none, 1 relu, 2 gelu(erf)
   };
-  static constexpr int kPasses = 1;
-  static constexpr int kColumnSplit = 2;
   __device__ __forceinline__ void begin(const Params&, int, int, int) {}
   __device__ __forceinline__ void end(const Params&, int, int, int) {}
   __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int /*pass*/) {
@@ -93,14 +100,12 @@ struct EpiBiasAct {
 // pixels, so each half-warp (16 lanes) is exactly one frame; a halving butterfly leaves lane j of
 // the half-warp with the sums of columns 2j, 2j+1 of the chunk.
 // -------------------------------------------------------------------------------------------
-struct EpiConvPool16 {
+struct EpiConvPool16 : EpiDefaults {
   struct Params {
     const float* bias;        // [N]
     __nv_bfloat16* out_bf16;  // [frames][N]
     int frames, N;
   };
-  static constexpr int kPasses = 1;
-  static constexpr int kColumnSplit = 2;
   __device__ __forceinline__ void begin(const Params&, int, int, int) {}
   __device__ __forceinline__ void end(const Params&, int, int, int) {}
   __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int /*pass*/) {
@@ -137,7 +142,7 @@ struct EpiConvPool16 {
 // BLOCK_N covers the whole embedding row, so the thread that owns the row owns the whole reduction:
 // pass 0 accumulates the squared norm, pass 1 re-reads the accumulator from TMEM and writes the scaled row.
 // -------------------------------------------------------------------------------------------
-struct EpiBiasL2Norm {
+struct EpiBiasL2Norm : EpiDefaults {
   struct Params {
     const float* bias;  // [N]
     float* out_f32;     // [M][N]
@@ -178,7 +183,7 @@ struct EpiBiasL2Norm {
 // Survivors are rare, so one global atomic per hit is cheaper than any staging. `count` keeps
 // counting past `capacity` so the caller can size a retry.
 // -------------------------------------------------------------------------------------------
-struct EpiJoinThreshold {
+struct EpiJoinThreshold : EpiDefaults {
   struct Params {
     float thr;
     long long q_rows, db_rows;  // valid extents
@@ -189,8 +194,6 @@ struct EpiJoinThreshold {
     unsigned long long* count;
     long long capacity;
   };
-  static constexpr int kPasses = 1;
-  static constexpr int kColumnSplit = 2;
   __device__ __forceinline__ void begin(const Params&, int, int, int) {}
   __device__ __forceinline__ void end(const Params&, int, int, int) {}
   __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int /*pass*/) {

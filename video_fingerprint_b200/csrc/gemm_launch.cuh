@@ -21,18 +21,19 @@ template <int BLOCK_N, int BLOCK_K, int STAGES, class Epi>
 inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& shape,
                                const typename Epi::Params& ep, cudaStream_t stream) {
   using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES>;
-  static_assert(L::kTotal <= 232448, "shared memory budget");
+  constexpr int kSmem = L::kTotal + Epi::kExtraSmemBytes;
+  static_assert(kSmem <= 232448, "shared memory budget");
   auto kernel = gemm_tcgen05_kernel<BLOCK_N, BLOCK_K, STAGES, Epi>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int total = shape.m_tiles * shape.n_tiles;
+  const int total = shape.row_resident ? shape.m_tiles * shape.n_segments : shape.m_tiles * shape.n_tiles;
   if (total <= 0) return cudaSuccess;
   const int grid = total < device_sm_count() ? total : device_sm_count();
-  kernel<<<grid, gemm_threads<BLOCK_N, Epi>(), L::kTotal, stream>>>(ta, tb, shape, ep);
+  kernel<<<grid, gemm_threads<BLOCK_N, Epi>(), kSmem, stream>>>(ta, tb, shape, ep);
   return cudaGetLastError();
 }
 
@@ -47,6 +48,8 @@ inline GemmShape plain_shape(long long M, int N, int K, int block_n, int block_k
   s.frames_per_tile = 1;
   s.tile_out_rows = 0;
   s.h_mul = 0;
+  s.row_resident = 0;
+  s.n_segments = 1;
   return s;
 }
 

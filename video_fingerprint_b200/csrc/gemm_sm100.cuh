@@ -30,6 +30,11 @@ struct GemmShape {
   int n_tiles;     // number of BLOCK_N column tiles
   int k_blocks;    // K / BLOCK_K
   int group_m;     // rasterisation: tiles are walked in groups of `group_m` row tiles (L2 reuse)
+  // schedule 1 ("row-block resident", used by the top-k search): a work item is one 128-row tile x one of
+  // `n_segments` contiguous column ranges; a CTA walks the item's column tiles in ascending order so a
+  // row-reducing epilogue can keep per-row state across them. Concurrent CTAs stream the same columns -> L2 reuse.
+  int row_resident;
+  int n_segments;
   // A operand addressing
   int a_conv;           // 0: rows are GEMM rows; 1: 4-D box (C, W, H, frame) over an NHWC activation tensor
   int tiles_per_frame;  // conv: row tiles per frame (>=1) ...
@@ -53,6 +58,44 @@ __device__ __forceinline__ void tile_coords(const GemmShape& s, int t, int& mt, 
   nt = r / gm;
 }
 
+// The tile sequence of one CTA; all three warp roles instantiate it and therefore see identical sequences.
+struct TileWalk {
+  const GemmShape& s;
+  int cur, stride, limit;       // schedule 0: tile index; schedule 1: work-item index
+  int nt, nt_end, mt, seg;      // schedule 1: position inside the item
+  __device__ TileWalk(const GemmShape& shape, int cta, int n_cta)
+      : s(shape), cur(cta), stride(n_cta), limit(shape.row_resident ? shape.m_tiles * shape.n_segments : shape.m_tiles * shape.n_tiles),
+        nt(0), nt_end(0), mt(0), seg(0) {}
+  // returns false when the CTA is done; first/last flag the first/last column tile of a work item
+  __device__ bool next(int& out_mt, int& out_nt, bool& first, bool& last) {
+    if (!s.row_resident) {
+      if (cur >= limit) return false;
+      tile_coords(s, cur, out_mt, out_nt);
+      cur += stride;
+      first = last = true;
+      return true;
+    }
+    if (nt >= nt_end) {
+      if (cur >= limit) return false;
+      mt = cur / s.n_segments;
+      seg = cur - mt * s.n_segments;
+      const int per = (s.n_tiles + s.n_segments - 1) / s.n_segments;
+      nt = seg * per;
+      nt_end = min(nt + per, s.n_tiles);
+      cur += stride;
+      first = true;
+      if (nt >= nt_end) { nt_end = nt + 1; }  // degenerate empty segment: still one (fully out-of-range) tile
+    } else {
+      first = false;
+    }
+    out_mt = mt;
+    out_nt = nt;
+    ++nt;
+    last = nt >= nt_end;
+    return true;
+  }
+};
+
 template <int BLOCK_N, int BLOCK_K, int STAGES>
 struct GemmSmemLayout {
   static constexpr int kRowBytes = BLOCK_K * 2;
@@ -60,7 +103,8 @@ struct GemmSmemLayout {
   static constexpr int kBBytes = BLOCK_N * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = 256;
-  static constexpr int kTotal = STAGES * kStageBytes + kBarrierBytes + 1024 /*alignment slack*/;
+  static constexpr int kCore = STAGES * kStageBytes + kBarrierBytes;
+  static constexpr int kTotal = kCore + 1024 /*alignment slack*/;
 };
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, class Epilogue>
@@ -86,7 +130,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = shape.m_tiles * shape.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -115,9 +158,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int mt, nt;
-        tile_coords(shape, t, mt, nt);
+      TileWalk walk(shape, blockIdx.x, gridDim.x);
+      int mt, nt;
+      bool first, last;
+      while (walk.next(mt, nt, first, last)) {
         int frame0 = 0, oh0 = 0;
         if (shape.a_conv) {
           if (shape.tiles_per_frame > 1) {
@@ -148,7 +192,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+      TileWalk walk(shape, blockIdx.x, gridDim.x);
+      int mt, nt;
+      bool first, last;
+      for (; walk.next(mt, nt, first, last); ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -178,15 +225,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int row = quarter * 32 + lane;
     const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
     int local = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-      int mt, nt;
-      tile_coords(shape, t, mt, nt);
+    TileWalk walk(shape, blockIdx.x, gridDim.x);
+    int mt, nt;
+    bool first, last;
+    Epilogue epi;
+    uint8_t* extra_smem = smem + L::kCore;
+    for (; walk.next(mt, nt, first, last); ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
+      if (first) epi.item_begin(ep, mt, walk.seg, row, extra_smem);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-      Epilogue epi;
       epi.begin(ep, mt, nt, row);
 #pragma unroll 1
       for (int pass = 0; pass < Epilogue::kPasses; ++pass) {  // row-wise reductions re-read the accumulator
@@ -202,6 +252,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (last) epi.item_end(ep, mt, walk.seg, row, extra_smem);
     }
   }
 

@@ -1,20 +1,331 @@
-// Flat inner-product top-k (placeholder until the screen + exact re-score pipeline lands).
+// Exact flat inner-product top-k (the arithmetic of faiss.IndexFlatIP.search, fingerprint.py:524-528):
+//
+//   1. screen   - the tcgen05 GEMM runs on bf16 copies with the "row-block resident" schedule; EpiTopK keeps,
+//                 per query row, the 64 best APPROXIMATE scores seen over the row's column segment (sorted
+//                 list in shared memory, one column of it per epilogue thread);
+//   2. merge    - per query row, the segment lists are merged to the 64 best approximate candidates, which
+//                 are re-scored EXACTLY in fp32 and ranked by (score desc, index asc); the top k are written;
+//   3. proof    - every database row outside the candidate list has approximate score <= a64 (the worst kept
+//                 one), hence exact score <= a64 + margin. If the exact k-th score beats that bound the result
+//                 is provably the exact top-k; otherwise the row is flagged ...
+//   4. fallback - ... and recomputed by a plain fp32 scan of the whole database (threshold = the exact k-th
+//                 score found so far, which every true top-k member must reach), then ranked again.
 #pragma once
 #include <string>
 
 #include "gemm_launch.cuh"
+#include "token_kernels.cuh"
 
 namespace vfp {
 
-inline size_t topk_workspace_bytes(int64_t n_q, int64_t n_db, int k) {
-  (void)n_q; (void)n_db; (void)k;
-  return 1024;
+constexpr int kTopKCand = 64;        // approximate candidates kept per query row
+constexpr int kTopKMaxK = 32;
+constexpr int kTopKMaxSegments = 32;
+constexpr int kTopKBucket = 512;     // exact-fallback candidates per flagged row
+constexpr int kTopKMaxFlagged = 8192;
+
+struct EpiTopK : EpiDefaults {
+  struct Params {
+    long long q_rows, db_rows;
+    int n_segments;
+    float* part_s;  // [m_tiles*128][n_segments][kTopKCand] approximate scores, descending
+    int* part_i;    //   "  database indices (-1 = empty)
+  };
+  static constexpr int kColumnSplit = 1;
+  static constexpr int kExtraSmemBytes = 2 * kTopKCand * 128 * 4;
+  float kth;
+  __device__ __forceinline__ void begin(const Params&, int, int, int) {}
+  __device__ __forceinline__ void end(const Params&, int, int, int) {}
+  __device__ __forceinline__ void item_begin(const Params&, int, int, int row, uint8_t* extra) {
+    float* ls = reinterpret_cast<float*>(extra) + row;
+    int* li = reinterpret_cast<int*>(extra + kTopKCand * 128 * 4) + row;
+    for (int c = 0; c < kTopKCand; ++c) {
+      ls[c * 128] = -INFINITY;
+      li[c * 128] = -1;
+    }
+    kth = -INFINITY;
+    smem_ls = ls;
+    smem_li = li;
+  }
+  __device__ __forceinline__ void item_end(const Params& p, int mt, int seg, int row, uint8_t*) {
+    const size_t base = (((size_t)mt * 128 + row) * p.n_segments + seg) * kTopKCand;
+    for (int c = 0; c < kTopKCand; ++c) {
+      p.part_s[base + c] = smem_ls[c * 128];
+      p.part_i[base + c] = smem_li[c * 128];
+    }
+  }
+  __device__ __forceinline__ void chunk(const Params& p, int, int col0, int, uint32_t (&v)[32], int) {
+    if (col0 >= p.db_rows) return;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+    if (!(mx > kth)) return;
+#pragma unroll 1
+    for (int i = 0; i < 32; ++i) {
+      const float s = __uint_as_float(v[i]);
+      const int j = col0 + i;
+      if (s > kth && j < p.db_rows) {  // strict: columns arrive in ascending order, ties keep the smaller index
+        int pos = kTopKCand - 1;
+        while (pos > 0 && smem_ls[(pos - 1) * 128] < s) {
+          smem_ls[pos * 128] = smem_ls[(pos - 1) * 128];
+          smem_li[pos * 128] = smem_li[(pos - 1) * 128];
+          --pos;
+        }
+        smem_ls[pos * 128] = s;
+        smem_li[pos * 128] = j;
+        kth = smem_ls[(kTopKCand - 1) * 128];
+      }
+    }
+  }
+  float* smem_ls;
+  int* smem_li;
+};
+
+__device__ __forceinline__ bool topk_better(float sa, int ia, float sb, int ib) {
+  return sa > sb || (sa == sb && ia < ib);
 }
 
-inline int topk_run(const float*, const float*, int64_t, int64_t, int, float, float*, int64_t*, unsigned long long*,
-                    uint8_t*, cudaStream_t, std::string* err) {
-  *err = "not implemented yet";
-  return 1;
+// exact fp32 dot of the warp's query (8 values per lane in qv) with database row j
+__device__ __forceinline__ float warp_dot256(const float (&qv)[8], const float* __restrict__ db, long long j, int lane) {
+  const float4* r = reinterpret_cast<const float4*>(db + (size_t)j * 256) + lane * 2;
+  const float4 a = r[0], b = r[1];
+  float s = qv[0] * a.x + qv[1] * a.y + qv[2] * a.z + qv[3] * a.w + qv[4] * b.x + qv[5] * b.y + qv[6] * b.z + qv[7] * b.w;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+// One warp per query row: merge segment lists -> 64 approximate candidates -> exact re-score -> rank -> top k.
+__global__ void __launch_bounds__(256)
+topk_merge_rescore_kernel(const float* __restrict__ q, const float* __restrict__ db, long long n_q, long long n_db, int k,
+                          int n_segments, const float* __restrict__ part_s, const int* __restrict__ part_i, float margin,
+                          float* __restrict__ out_s, long long* __restrict__ out_idx, int* __restrict__ flagged_rows,
+                          float* __restrict__ flagged_tau, unsigned long long* __restrict__ flags /*[0]=flagged,[1]=overflow*/) {
+  const int lane = threadIdx.x & 31;
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_q) return;
+  const float* ps = part_s + (size_t)row * n_segments * kTopKCand;
+  const int* pi = part_i + (size_t)row * n_segments * kTopKCand;
+
+  // ---- merge: lane s walks segment s (each list is sorted); 64 rounds of warp arg-max over the heads ----
+  int head = 0;
+  float cs[2] = {-INFINITY, -INFINITY};  // candidate c lives in lane c % 32, slot c / 32
+  int ci[2] = {-1, -1};
+  for (int c = 0; c < kTopKCand; ++c) {
+    float hs = -INFINITY;
+    int hi = 0x7fffffff;
+    if (lane < n_segments && head < kTopKCand) {
+      hs = ps[lane * kTopKCand + head];
+      hi = pi[lane * kTopKCand + head];
+      if (hi < 0) { hs = -INFINITY; hi = 0x7fffffff; }
+    }
+    float bs = hs;
+    int bi = hi, bl = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      const int ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (topk_better(os, oi, bs, bi)) { bs = os; bi = oi; bl = ol; }
+    }
+    if (bi == 0x7fffffff) break;  // all lists exhausted (n_db < 64)
+    if (lane == bl) ++head;
+    if (lane == (c & 31)) { cs[c >> 5] = bs; ci[c >> 5] = bi; }
+  }
+  // worst approximate score kept (lane 31, slot 1 = candidate 63); -inf if the list is not full
+  const float a_last = __shfl_sync(0xffffffffu, cs[1], 31);
+  const int i_last = __shfl_sync(0xffffffffu, ci[1], 31);
+
+  // ---- exact re-score ----
+  float qv[8];
+  {
+    const float4* r = reinterpret_cast<const float4*>(q + (size_t)row * 256) + lane * 2;
+    const float4 a = r[0], b = r[1];
+    qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = b.x; qv[5] = b.y; qv[6] = b.z; qv[7] = b.w;
+  }
+  float es[2] = {-INFINITY, -INFINITY};
+  for (int c = 0; c < kTopKCand; ++c) {
+    const int idx = __shfl_sync(0xffffffffu, ci[c >> 5], c & 31);
+    if (idx < 0) continue;  // warp-uniform
+    const float s = warp_dot256(qv, db, idx, lane);
+    if (lane == (c & 31)) es[c >> 5] = s;
+  }
+  // ---- rank by (exact score desc, index asc) ----
+  int rank[2] = {0, 0};
+  for (int c = 0; c < kTopKCand; ++c) {
+    const float s = __shfl_sync(0xffffffffu, es[c >> 5], c & 31);
+    const int idx = __shfl_sync(0xffffffffu, ci[c >> 5], c & 31);
+    if (idx < 0) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (ci[h] >= 0 && topk_better(s, idx, es[h], ci[h])) ++rank[h];
+  }
+  float kth_exact = -INFINITY;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (ci[h] >= 0 && rank[h] < k) {
+      out_s[(size_t)row * k + rank[h]] = es[h];
+      out_idx[(size_t)row * k + rank[h]] = ci[h];
+      if (rank[h] == k - 1) kth_exact = es[h];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kth_exact = fmaxf(kth_exact, __shfl_xor_sync(0xffffffffu, kth_exact, o));
+  // ---- proof of exactness ----
+  const bool list_is_everything = i_last < 0;  // fewer than 64 database rows exist in total
+  const bool proven = list_is_everything || (kth_exact > a_last + margin);
+  if (!proven && lane == 0) {
+    const unsigned long long slot = atomicAdd(&flags[0], 1ull);
+    if (slot < (unsigned long long)kTopKMaxFlagged) {
+      flagged_rows[slot] = (int)row;
+      flagged_tau[slot] = kth_exact;
+    } else {
+      atomicAdd(&flags[1], 1ull);
+    }
+  }
+}
+
+// Exact fallback, pass 1: for every flagged query, scan ALL database rows in fp32 and bucket those with
+// score >= tau (the exact k-th score among the screened candidates - a lower bound of the true k-th score).
+__global__ void __launch_bounds__(256)
+topk_fallback_scan_kernel(const float* __restrict__ q, const float* __restrict__ db, long long n_db,
+                          const int* __restrict__ flagged_rows, const float* __restrict__ flagged_tau,
+                          const unsigned long long* __restrict__ flags, int* __restrict__ bucket_cnt,
+                          float* __restrict__ bucket_s, int* __restrict__ bucket_i, unsigned long long* __restrict__ flags_rw) {
+  const int lane = threadIdx.x & 31;
+  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  unsigned long long nf = flags[0];
+  if (nf > (unsigned long long)kTopKMaxFlagged) nf = kTopKMaxFlagged;
+  for (unsigned long long f = 0; f < nf; ++f) {
+    const int row = flagged_rows[f];
+    const float tau = flagged_tau[f];
+    float qv[8];
+    const float4* r = reinterpret_cast<const float4*>(q + (size_t)row * 256) + lane * 2;
+    const float4 a = r[0], b = r[1];
+    qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = b.x; qv[5] = b.y; qv[6] = b.z; qv[7] = b.w;
+    for (long long j = warp0; j < n_db; j += warps) {
+      const float s = warp_dot256(qv, db, j, lane);
+      if (lane == 0 && s >= tau) {
+        const int slot = atomicAdd(&bucket_cnt[f], 1);
+        if (slot < kTopKBucket) {
+          bucket_s[f * kTopKBucket + slot] = s;
+          bucket_i[f * kTopKBucket + slot] = (int)j;
+        } else if (slot == kTopKBucket) {
+          atomicAdd(&flags_rw[1], 1ull);
+        }
+      }
+    }
+  }
+}
+
+// Exact fallback, pass 2: rank each flagged row's bucket and overwrite its output row.
+__global__ void __launch_bounds__(128)
+topk_fallback_rank_kernel(int k, const int* __restrict__ flagged_rows, const unsigned long long* __restrict__ flags,
+                          const int* __restrict__ bucket_cnt, const float* __restrict__ bucket_s, const int* __restrict__ bucket_i,
+                          float* __restrict__ out_s, long long* __restrict__ out_idx) {
+  unsigned long long nf = flags[0];
+  if (nf > (unsigned long long)kTopKMaxFlagged) nf = kTopKMaxFlagged;
+  for (unsigned long long f = blockIdx.x; f < nf; f += gridDim.x) {
+    const int row = flagged_rows[f];
+    const int n = min(bucket_cnt[f], kTopKBucket);
+    const float* bs = bucket_s + f * kTopKBucket;
+    const int* bi = bucket_i + f * kTopKBucket;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+      const float s = bs[c];
+      const int idx = bi[c];
+      int rank = 0;
+      for (int o = 0; o < n; ++o) rank += topk_better(bs[o], bi[o], s, idx) ? 1 : 0;
+      if (rank < k) {
+        out_s[(size_t)row * k + rank] = s;
+        out_idx[(size_t)row * k + rank] = idx;
+      }
+    }
+  }
+}
+
+struct TopKWs {
+  size_t qbf, dbbf, part_s, part_i, flagged_rows, flagged_tau, bucket_cnt, bucket_s, bucket_i, flags, total;
+  int n_segments;
+  long long rows_padded;
+};
+inline TopKWs topk_ws_layout(int64_t n_q, int64_t n_db) {
+  TopKWs L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off = (off + bytes + 1023) / 1024 * 1024;
+    return o;
+  };
+  const int64_t m_tiles = (n_q + 127) / 128;
+  const int64_t n_tiles = (n_db + 255) / 256;
+  // enough work items to fill the GPU a few times over, without splitting more than necessary
+  int seg = 1;
+  while (seg < kTopKMaxSegments && m_tiles * seg < 4 * 148 && seg * 2 <= n_tiles) seg *= 2;
+  L.n_segments = seg;
+  L.rows_padded = m_tiles * 128;
+  L.qbf = take((size_t)n_q * 512);
+  L.dbbf = take((size_t)n_db * 512);
+  L.part_s = take((size_t)L.rows_padded * seg * kTopKCand * 4);
+  L.part_i = take((size_t)L.rows_padded * seg * kTopKCand * 4);
+  L.flagged_rows = take((size_t)kTopKMaxFlagged * 4);
+  L.flagged_tau = take((size_t)kTopKMaxFlagged * 4);
+  L.bucket_cnt = take((size_t)kTopKMaxFlagged * 4);
+  L.bucket_s = take((size_t)kTopKMaxFlagged * kTopKBucket * 4);
+  L.bucket_i = take((size_t)kTopKMaxFlagged * kTopKBucket * 4);
+  L.flags = take(64);
+  L.total = off;
+  return L;
+}
+inline size_t topk_workspace_bytes(int64_t n_q, int64_t n_db, int k) {
+  (void)k;
+  if (n_q <= 0 || n_db <= 0) return 0;
+  return topk_ws_layout(n_q, n_db).total;
+}
+
+inline int topk_run(const float* q, const float* db, int64_t n_q, int64_t n_db, int k, float margin, float* out_s,
+                    int64_t* out_idx, unsigned long long* flags_out, uint8_t* ws, cudaStream_t st, std::string* err) {
+  const TopKWs L = topk_ws_layout(n_q, n_db);
+  const bool self = (q == db && n_q == n_db);
+  __nv_bfloat16* qbf = reinterpret_cast<__nv_bfloat16*>(ws + L.qbf);
+  __nv_bfloat16* dbbf = self ? qbf : reinterpret_cast<__nv_bfloat16*>(ws + L.dbbf);
+  float* part_s = reinterpret_cast<float*>(ws + L.part_s);
+  int* part_i = reinterpret_cast<int*>(ws + L.part_i);
+  int* flagged_rows = reinterpret_cast<int*>(ws + L.flagged_rows);
+  float* flagged_tau = reinterpret_cast<float*>(ws + L.flagged_tau);
+  int* bucket_cnt = reinterpret_cast<int*>(ws + L.bucket_cnt);
+  float* bucket_s = reinterpret_cast<float*>(ws + L.bucket_s);
+  int* bucket_i = reinterpret_cast<int*>(ws + L.bucket_i);
+  unsigned long long* flags = reinterpret_cast<unsigned long long*>(ws + L.flags);
+  auto ck = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess) { *err = std::string(what) + ": " + cudaGetErrorString(e); return true; }
+    return false;
+  };
+  if (ck(cudaMemsetAsync(flags, 0, 64, st), "memset") || ck(cudaMemsetAsync(bucket_cnt, 0, (size_t)kTopKMaxFlagged * 4, st), "memset"))
+    return 1;
+  f32_to_bf16_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, st>>>(q, qbf, n_q * 32);
+  if (!self) f32_to_bf16_kernel<<<(unsigned)((n_db * 32 + 255) / 256), 256, 0, st>>>(db, dbbf, n_db * 32);
+  CUtensorMap ta, tb;
+  if (make_tmap_rows_bf16(&ta, qbf, (uint64_t)n_q, 256, 256, 128, 64) || make_tmap_rows_bf16(&tb, dbbf, (uint64_t)n_db, 256, 256, 256, 64)) {
+    *err = "tensor map encode failed";
+    return 1;
+  }
+  GemmShape s = plain_shape(n_q, 0, 256, 256, 64, 1);
+  s.n_tiles = (int)((n_db + 255) / 256);
+  s.row_resident = 1;
+  s.n_segments = L.n_segments;
+  EpiTopK::Params ep{};
+  ep.q_rows = n_q; ep.db_rows = n_db; ep.n_segments = L.n_segments; ep.part_s = part_s; ep.part_i = part_i;
+  if (ck((launch_gemm<256, 64, 3, EpiTopK>(ta, tb, s, ep, st)), "screen launch")) return 1;
+  topk_merge_rescore_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, st>>>(q, db, n_q, n_db, k, L.n_segments, part_s, part_i, margin,
+                                                                               out_s, reinterpret_cast<long long*>(out_idx), flagged_rows,
+                                                                               flagged_tau, flags);
+  topk_fallback_scan_kernel<<<device_sm_count() * 8, 256, 0, st>>>(q, db, n_db, flagged_rows, flagged_tau, flags, bucket_cnt, bucket_s,
+                                                                   bucket_i, flags);
+  topk_fallback_rank_kernel<<<device_sm_count() * 2, 128, 0, st>>>(k, flagged_rows, flags, bucket_cnt, bucket_s, bucket_i, out_s,
+                                                                   reinterpret_cast<long long*>(out_idx));
+  if (ck(cudaMemcpyAsync(flags_out, flags, 16, cudaMemcpyDeviceToDevice, st), "copy flags") || ck(cudaGetLastError(), "top-k kernels")) return 1;
+  return 0;
 }
 
 }  // namespace vfp
