@@ -108,6 +108,7 @@ def dist_setup(n_gpus: int):
     if world > 1:
         import torch.distributed as dist
 
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return world, rank, local
@@ -155,6 +156,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1; the reference arm gets every host core
     threads = torch.get_num_threads()
     per_step = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
@@ -355,7 +357,7 @@ def run_ours(args):
         },
         "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "stage_ms_per_step": stages, "join": join, "clocks": clocks,
     }
-    if not args.no_cpu and world >= 1:
+    if not args.no_cpu and world == 1:
         r, n, dt = cpu_reference_rate(args.cpu_seconds, 2048)
         line["cpu_baseline"] = {
             "value": r, "unit": "videos/s", "cores": torch.get_num_threads(), "kind": "port",
