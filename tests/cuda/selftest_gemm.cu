@@ -179,8 +179,54 @@ static int run_conv(int frames) {
   return ok ? 0 : 1;
 }
 
+template <int BN, int BK, int ST, int KBLOCKS>
+static int run_bres(long long M, int N) {
+  const int K = KBLOCKS * BK;
+  std::vector<__nv_bfloat16> hA(M * K), hB((size_t)N * K);
+  std::vector<float> hbias(N);
+  for (auto& v : hA) v = f2b(frand());
+  for (auto& v : hB) v = f2b(frand());
+  for (auto& v : hbias) v = frand();
+  __nv_bfloat16 *dA, *dB;
+  float *dbias, *dO;
+  CK(cudaMalloc(&dA, hA.size() * 2));
+  CK(cudaMalloc(&dB, hB.size() * 2));
+  CK(cudaMalloc(&dbias, N * 4));
+  CK(cudaMalloc(&dO, M * N * 4));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias, hbias.data(), N * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dO, 0xFF, M * N * 4));
+  CUtensorMap ta, tb;
+  if (make_tmap_rows_bf16(&ta, dA, M, K, K, 128, BK) || make_tmap_rows_bf16(&tb, dB, N, K, K, BN, BK)) return 1;
+  GemmShape s = plain_shape(M, N, K, BN, BK, 4);
+  EpiBiasAct::Params ep{};
+  ep.bias = dbias; ep.out_f32 = dO; ep.ld_out = N; ep.M = (int)M; ep.N = N;
+  CK((launch_gemm_bres<BN, BK, ST, KBLOCKS, EpiBiasAct>(ta, tb, s, ep, 0)));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> hO(M * N);
+  CK(cudaMemcpy(hO.data(), dO, hO.size() * 4, cudaMemcpyDeviceToHost));
+  double max_err = 0;
+  for (long long m = 0; m < M; m += 7)
+    for (int n = 0; n < N; ++n) {
+      double acc = hbias[n];
+      for (int k = 0; k < K; ++k) acc += (double)b2f(hA[m * K + k]) * (double)b2f(hB[(size_t)n * K + k]);
+      const double e = fabs(acc - hO[m * N + n]);
+      if (!(e <= max_err)) max_err = e;
+    }
+  const bool ok = max_err < 2e-3;
+  printf("[b-resident BN=%d BK=%d KB=%d] M=%lld N=%d  max_abs_err=%.3e  %s\n", BN, BK, KBLOCKS, M, N, max_err, ok ? "OK" : "FAIL");
+  cudaFree(dA); cudaFree(dB); cudaFree(dbias); cudaFree(dO);
+  return ok ? 0 : 1;
+}
+
 int main() {
   int fails = 0;
+  fails += run_bres<256, 64, 4, 4>(300, 256);
+  fails += run_bres<256, 64, 4, 4>(40000, 768);     // several column tiles per CTA: B is reloaded mid-range
+  fails += run_bres<256, 64, 4, 4>(128 * 200, 1024);
+  fails += run_bres<128, 64, 4, 9>(5000, 128);
+  fails += run_bres<64, 64, 6, 6>(3000, 64);
   fails += run_plain<256, 64, 4>(128, 256, 64, 0, false);
   fails += run_plain<256, 64, 4>(128, 256, 256, 0, false);
   fails += run_plain<256, 64, 4>(300, 256, 256, 1, true);

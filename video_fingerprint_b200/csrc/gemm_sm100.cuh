@@ -265,4 +265,186 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+// =================================================================================================
+// B-resident variant. The profiles of the kernel above show it is bound by operand fill (L2 -> SMEM through
+// TMA, ~40-48 B/clk/SM), not by the MMA pipe: every 128-row tile re-fetches its whole B tile. Here the B operand
+// of the current column tile (all KB K-blocks: conv filters, a 256x256 weight block, a database tile of the join)
+// stays in shared memory while the CTA sweeps a CONTIGUOUS run of row tiles, so only A streams through the ring.
+// Tiles are numbered column-tile-major (u = nt * m_tiles + mt) and each CTA takes one contiguous range, hence
+// B is (re)loaded only when the range crosses into the next column tile.
+// =================================================================================================
+template <int BLOCK_N, int BLOCK_K, int STAGES, int KB>
+struct GemmBresSmemLayout {
+  static constexpr int kRowBytes = BLOCK_K * 2;
+  static constexpr int kABytes = kBlockM * kRowBytes;
+  static constexpr int kBBytes = BLOCK_N * kRowBytes;  // one K block of B
+  static constexpr int kCore = STAGES * kABytes + KB * kBBytes + 256;
+  static constexpr int kTotal = kCore + 1024;
+};
+
+template <int BLOCK_N, int BLOCK_K, int STAGES, int KB, class Epilogue>
+__global__ void __launch_bounds__(gemm_threads<BLOCK_N, Epilogue>(), 1)
+gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmShape shape, const typename Epilogue::Params ep) {
+  using L = GemmBresSmemLayout<BLOCK_N, BLOCK_K, STAGES, KB>;
+  constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
+                                 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * L::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kABytes + KB * L::kBBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;
+  uint64_t* b_full = bars + 2 * STAGES + 4;
+  uint64_t* b_empty = bars + 2 * STAGES + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const long long total = (long long)shape.m_tiles * shape.n_tiles;
+  const long long per = (total + gridDim.x - 1) / gridDim.x;
+  const long long u0 = (long long)blockIdx.x * per;
+  const long long u1 = min(total, u0 + per);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4 * gemm_column_split<BLOCK_N, Epilogue>());
+    }
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0, cur_nt = -1;
+      uint32_t phase = 0, b_phase = 0;
+      for (long long u = u0; u < u1; ++u) {
+        const int nt = (int)(u / shape.m_tiles);
+        const int mt = (int)(u - (long long)nt * shape.m_tiles);
+        if (nt != cur_nt) {
+          if (cur_nt >= 0) {  // the MMAs of the previous column tile must have drained before B is overwritten
+            mbar_wait(b_empty, b_phase);
+            b_phase ^= 1;
+          }
+          mbar_arrive_expect_tx(b_full, KB * L::kBBytes);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d(&tmap_b, b_full, smem_b + kb * L::kBBytes, kb * BLOCK_K, nt * BLOCK_N);
+          cur_nt = nt;
+        }
+        int frame0 = 0, oh0 = 0;
+        if (shape.a_conv) {
+          if (shape.tiles_per_frame > 1) {
+            frame0 = mt / shape.tiles_per_frame;
+            oh0 = (mt - frame0 * shape.tiles_per_frame) * shape.tile_out_rows;
+          } else {
+            frame0 = mt * shape.frames_per_tile;
+          }
+        }
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full_bar[stage], L::kABytes);
+          if (shape.a_conv) {
+            tma_load_4d(&tmap_a, &full_bar[stage], smem_a + stage * L::kABytes, shape.tap_c_blk[kb] * BLOCK_K,
+                        shape.tap_w[kb], shape.h_mul * oh0 + shape.tap_h[kb], frame0);
+          } else {
+            tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * L::kABytes, kb * BLOCK_K, mt * kBlockM);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+      int stage = 0, cur_nt = -1, local = 0;
+      uint32_t phase = 0, b_phase = 0;
+      for (long long u = u0; u < u1; ++u, ++local) {
+        const int nt = (int)(u / shape.m_tiles);
+        if (nt != cur_nt) {
+          mbar_wait(b_full, b_phase);
+          b_phase ^= 1;
+          cur_nt = nt;
+        }
+        const int acc = local & 1;
+        const uint32_t acc_phase = (local >> 1) & 1;
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc_kmajor<L::kRowBytes>(smem_u32(smem_a + stage * L::kABytes));
+          const uint64_t bdesc = umma_smem_desc_kmajor<L::kRowBytes>(smem_u32(smem_b + kb * L::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&acc_full[acc]);
+        if (u + 1 < u1 && (int)((u + 1) / shape.m_tiles) != nt) umma_commit(b_empty);
+      }
+    }
+  } else {
+    constexpr int kSplit = gemm_column_split<BLOCK_N, Epilogue>();
+    constexpr int kColsPerWarp = BLOCK_N / kSplit;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
+    int local = 0;
+    Epilogue epi;
+    for (long long u = u0; u < u1; ++u, ++local) {
+      const int nt = (int)(u / shape.m_tiles);
+      const int mt = (int)(u - (long long)nt * shape.m_tiles);
+      const int acc = local & 1;
+      const uint32_t acc_phase = (local >> 1) & 1;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+      epi.begin(ep, mt, nt, row);
+#pragma unroll 1
+      for (int pass = 0; pass < Epilogue::kPasses; ++pass) {
+#pragma unroll 1
+        for (int c = col_begin; c < col_begin + kColsPerWarp; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c, v);
+          tmem_ld_wait();
+          epi.chunk(ep, mt, nt * BLOCK_N + c, row, v, pass);
+        }
+      }
+      epi.end(ep, mt, nt, row);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 }  // namespace vfp

@@ -557,7 +557,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     }
     EpiBiasAct::Params ep{};
     ep.bias = w->c2_b; ep.out_bf16 = c2a; ep.ld_out = 64; ep.M = (int)(F * 256); ep.N = 64; ep.act = 1;
-    VFP_CUDA((launch_gemm<64, 64, 8, EpiBiasAct>(ta, w->tm_c2, s, ep, st)));
+    VFP_CUDA((launch_gemm_bres<64, 64, 6, 6, EpiBiasAct>(ta, w->tm_c2, s, ep, st)));
     g_prof.mark(kStConv2, st);
   }
   {  // conv3: 16x16x64 -> 8x8x128 through a stride-2 box, tile = 2 frames
@@ -568,7 +568,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     conv_taps_strided(&s, 1);
     EpiBiasAct::Params ep{};
     ep.bias = w->c3_b; ep.out_bf16 = c3a; ep.ld_out = 128; ep.M = (int)(F * 64); ep.N = 128; ep.act = 1;
-    VFP_CUDA((launch_gemm<128, 64, 6, EpiBiasAct>(ta, w->tm_c3, s, ep, st)));
+    VFP_CUDA((launch_gemm_bres<128, 64, 4, 9, EpiBiasAct>(ta, w->tm_c3, s, ep, st)));
     g_prof.mark(kStConv3, st);
   }
   {  // conv4: 8x8x128 -> 4x4x256 + ReLU + global average pool, tile = 8 frames
@@ -633,7 +633,11 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     CUtensorMap tma;
     if (make_tmap_rows_bf16(&tma, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 64)) return fail("tensor map encode failed (tokens)");
     GemmShape s = plain_shape(M, N, K, 256, 64, 32);
-    VFP_CUDA((launch_gemm<256, 64, 4, EpiBiasAct>(tma, tb, s, ep, st)));
+    if (K == 256) {  // the whole 256x256 weight block of a column tile stays in shared memory
+      VFP_CUDA((launch_gemm_bres<256, 64, 4, 4, EpiBiasAct>(tma, tb, s, ep, st)));
+    } else {
+      VFP_CUDA((launch_gemm<256, 64, 4, EpiBiasAct>(tma, tb, s, ep, st)));
+    }
     return 0;
   };
   {
@@ -809,7 +813,7 @@ int vfp_join_threshold(const float* q, const float* db, int64_t n_q, int64_t n_d
   ep.thr = thr - screen_margin;
   ep.q_rows = n_q; ep.db_rows = n_db; ep.q_row0 = q_row0;
   ep.out_i = cand_i; ep.out_j = cand_j; ep.out_s = cand_s; ep.count = cand_count; ep.capacity = cand_cap;
-  VFP_CUDA((launch_gemm<256, 64, 4, EpiJoinThreshold>(ta, tb, s, ep, st)));
+  VFP_CUDA((launch_gemm_bres<256, 64, 4, 4, EpiJoinThreshold>(ta, tb, s, ep, st)));
   rescore_pairs_kernel<<<device_sm_count() * 4, 256, 0, st>>>(q, db, dim, q_row0, cand_i, cand_j, cand_count, cand_cap, thr,
                                                               out_i, out_j, out_s, counts, capacity);
   // counts[1] = candidate count (device-side copy so the caller reads both with one transfer)
