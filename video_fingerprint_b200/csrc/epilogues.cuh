@@ -17,6 +17,8 @@ struct EpiDefaults {
   static constexpr int kPasses = 1;
   static constexpr int kColumnSplit = 2;
   static constexpr int kExtraSmemBytes = 0;
+  template <class P> __device__ __forceinline__ void setup(const P&, uint8_t*, int, int) {}
+  template <class P> __device__ __forceinline__ void finish(const P&, int) {}
   template <class P> __device__ __forceinline__ void item_begin(const P&, int, int, int, uint8_t*) {}
   template <class P> __device__ __forceinline__ void item_end(const P&, int, int, int, uint8_t*) {}
 };
@@ -93,6 +95,89 @@ struct EpiBiasAct : EpiDefaults {
     }
   }
   static constexpr int kBlockMRows = 128;
+};
+
+// -------------------------------------------------------------------------------------------
+// y = act(acc + bias) written through the TMA unit. A thread owns a ROW of the accumulator, so direct global
+// stores put 32 different cache lines into every store instruction (ncu: 32 sectors/request, LSU-bound
+// epilogue). Here each warp packs its 32x32 chunk into a swizzled shared-memory staging tile (conflict-free
+// 16-byte stores) and one lane hands it to cp.async.bulk.tensor: full-line writes, no LSU traffic, and
+// out-of-range rows of the last tile are clipped by the tensor map.
+// -------------------------------------------------------------------------------------------
+template <bool BF16_OUT>
+struct EpiBiasActTma : EpiDefaults {
+  struct Params {
+    alignas(64) CUtensorMap tmap_out;  // [M][N] row-major, box = 32 cols x 32 rows, swizzle = row bytes of the box
+    const float* bias;                 // [N] or null
+    int N;
+    int act;                           // 0 none, 1 relu, 2 gelu(erf)
+  };
+  static constexpr int kChunkBytes = BF16_OUT ? 2048 : 4096;
+  static constexpr int kBuffers = 2;
+  static constexpr int kExtraSmemBytes = 8 * kBuffers * kChunkBytes;
+  uint8_t* stage;
+  int buf;
+  __device__ __forceinline__ void setup(const Params&, uint8_t* extra, int warp_slot, int) {
+    stage = extra + warp_slot * (kBuffers * kChunkBytes);
+    buf = 0;
+  }
+  __device__ __forceinline__ void finish(const Params&, int lane) {
+    if (lane == 0) tma_store_wait_read<0>();  // staging must stay valid until the TMA unit has read it
+  }
+  __device__ __forceinline__ void begin(const Params&, int, int, int) {}
+  __device__ __forceinline__ void end(const Params&, int, int, int) {}
+  __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int) {
+    if (col0 >= p.N) return;  // warp-uniform
+    const int lane = row & 31;
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+    if (p.bias) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+        x[i] += b.x; x[i + 1] += b.y; x[i + 2] += b.z; x[i + 3] += b.w;
+      }
+    }
+    if (p.act == 1) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
+    } else if (p.act == 2) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = gelu_erf(x[i]);
+    }
+    uint8_t* dst = stage + buf * kChunkBytes;
+    if (lane == 0) tma_store_wait_read<kBuffers - 1>();  // the store that last used this buffer has read it
+    __syncwarp();
+    if constexpr (BF16_OUT) {
+      // 64-byte rows, SWIZZLE_64B: 16-byte chunk c of row r lives at chunk c ^ ((r >> 1) & 3)
+      uint8_t* r0 = dst + lane * 64;
+      const int sw = (lane >> 1) & 3;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint4 q;
+        q.x = pack_bf16x2(x[8 * c + 0], x[8 * c + 1]);
+        q.y = pack_bf16x2(x[8 * c + 2], x[8 * c + 3]);
+        q.z = pack_bf16x2(x[8 * c + 4], x[8 * c + 5]);
+        q.w = pack_bf16x2(x[8 * c + 6], x[8 * c + 7]);
+        *reinterpret_cast<uint4*>(r0 + ((c ^ sw) << 4)) = q;
+      }
+    } else {
+      // 128-byte rows, SWIZZLE_128B: chunk c of row r lives at chunk c ^ (r & 7)
+      uint8_t* r0 = dst + lane * 128;
+      const int sw = lane & 7;
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(r0 + ((c ^ sw) << 4)) = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&p.tmap_out, dst, col0, mt * 128 + (row & ~31));
+      tma_store_commit();
+    }
+    buf ^= 1;
+  }
 };
 
 // -------------------------------------------------------------------------------------------

@@ -41,20 +41,20 @@ template <int BLOCK_N, int BLOCK_K, int STAGES, int KB, class Epi>
 inline cudaError_t launch_gemm_bres(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& shape,
                                     const typename Epi::Params& ep, cudaStream_t stream) {
   using L = GemmBresSmemLayout<BLOCK_N, BLOCK_K, STAGES, KB>;
-  static_assert(L::kTotal <= 232448, "shared memory budget");
-  static_assert(Epi::kExtraSmemBytes == 0, "row-state epilogues use the generic kernel");
+  constexpr int kSmem = L::kTotal + Epi::kExtraSmemBytes;
+  static_assert(kSmem <= 232448, "shared memory budget");
   if (shape.k_blocks != KB) return cudaErrorInvalidValue;
   auto kernel = gemm_bres_tcgen05_kernel<BLOCK_N, BLOCK_K, STAGES, KB, Epi>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   const long long total = (long long)shape.m_tiles * shape.n_tiles;
   if (total <= 0) return cudaSuccess;
   const int grid = total < device_sm_count() ? (int)total : device_sm_count();
-  kernel<<<grid, gemm_threads<BLOCK_N, Epi>(), L::kTotal, stream>>>(ta, tb, shape, ep);
+  kernel<<<grid, gemm_threads<BLOCK_N, Epi>(), kSmem, stream>>>(ta, tb, shape, ep);
   return cudaGetLastError();
 }
 

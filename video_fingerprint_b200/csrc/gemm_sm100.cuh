@@ -104,13 +104,14 @@ struct GemmSmemLayout {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kBarrierBytes = 256;
   static constexpr int kCore = STAGES * kStageBytes + kBarrierBytes;
-  static constexpr int kTotal = kCore + 1024 /*alignment slack*/;
+  static constexpr int kCoreAligned = (kCore + 1023) / 1024 * 1024;  // epilogue staging starts 1024-aligned
+  static constexpr int kTotal = kCoreAligned + 1024 /*alignment slack*/;
 };
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, class Epilogue>
 __global__ void __launch_bounds__(gemm_threads<BLOCK_N, Epilogue>(), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmShape shape, const typename Epilogue::Params ep) {
+                    const GemmShape shape, const __grid_constant__ typename Epilogue::Params ep) {
   using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES>;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32 || BLOCK_K == 16, "BLOCK_K");
@@ -229,7 +230,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     int mt, nt;
     bool first, last;
     Epilogue epi;
-    uint8_t* extra_smem = smem + L::kCore;
+    uint8_t* extra_smem = smem + L::kCoreAligned;
+    epi.setup(ep, extra_smem, warp - 2, lane);
     for (; walk.next(mt, nt, first, last); ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
@@ -254,6 +256,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (last) epi.item_end(ep, mt, walk.seg, row, extra_smem);
     }
+    epi.finish(ep, lane);
   }
 
   __syncwarp();
@@ -279,13 +282,14 @@ struct GemmBresSmemLayout {
   static constexpr int kABytes = kBlockM * kRowBytes;
   static constexpr int kBBytes = BLOCK_N * kRowBytes;  // one K block of B
   static constexpr int kCore = STAGES * kABytes + KB * kBBytes + 256;
-  static constexpr int kTotal = kCore + 1024;
+  static constexpr int kCoreAligned = (kCore + 1023) / 1024 * 1024;
+  static constexpr int kTotal = kCoreAligned + 1024;
 };
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, int KB, class Epilogue>
 __global__ void __launch_bounds__(gemm_threads<BLOCK_N, Epilogue>(), 1)
 gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                         const GemmShape shape, const typename Epilogue::Params ep) {
+                         const GemmShape shape, const __grid_constant__ typename Epilogue::Params ep) {
   using L = GemmBresSmemLayout<BLOCK_N, BLOCK_K, STAGES, KB>;
   constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
                                  : (2 * BLOCK_N <= 256) ? 256 : 512;
@@ -412,6 +416,7 @@ gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
     int local = 0;
     Epilogue epi;
+    epi.setup(ep, smem + L::kCoreAligned, warp - 2, lane);
     for (long long u = u0; u < u1; ++u, ++local) {
       const int nt = (int)(u / shape.m_tiles);
       const int mt = (int)(u - (long long)nt * shape.m_tiles);
@@ -436,6 +441,7 @@ gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
     }
+    epi.finish(ep, lane);
   }
 
   __syncwarp();

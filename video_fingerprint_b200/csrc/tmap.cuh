@@ -50,6 +50,22 @@ inline int make_tmap_rows_bf16(CUtensorMap* out, const void* base, uint64_t rows
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
+// Row-major output matrix [rows][cols] written by the epilogue in 32-column x 32-row boxes (see EpiBiasActTma).
+inline int make_tmap_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, bool bf16) {
+  PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  const uint64_t esz = bf16 ? 2 : 4;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * esz};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+                   gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
 // bf16 NHWC activation tensor [frames][H][W][C] read as the A operand of an implicit-GEMM convolution:
 // one box = (c_box channels) x (out_w positions along W) x (out_h positions along H) x (n_box frames), visiting
 // every `stride`-th pixel along W and H (stride 2 = the 3x3/stride-2 convolutions; stride 1 = a space-to-depth

@@ -31,17 +31,34 @@ __global__ void token_map_kernel(const int* __restrict__ cu, int n_clips, int n_
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm over 256 channels, fp32 in -> bf16 out. One warp per token, 8 channels per lane.
+// (x += delta) ; y = LayerNorm(x) over 256 channels. fp32 residual stream in/out, bf16 normalised copy out.
+// The residual GEMMs (attention out-projection, MLP down-projection) emit their result as a bf16 `delta` through
+// the TMA store path; the add into the fp32 stream happens here, where the row is being read anyway, instead of
+// in the GEMM epilogue (whose row-per-thread layout makes fp32 read-modify-write uncoalesced).
+// One warp per token, 8 channels per lane.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                      __nv_bfloat16* __restrict__ y, int n_tokens) {
+add_layernorm_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta /*nullable*/,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                          int n_tokens) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_tokens) return;
-  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)warp * kDim) + lane * 2;
+  float4* xr = reinterpret_cast<float4*>(x + (size_t)warp * kDim) + lane * 2;
   const float4 a = xr[0], b = xr[1];
   float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (delta) {
+    const uint4 d = reinterpret_cast<const uint4*>(delta + (size_t)warp * kDim)[lane];
+    const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(dp[e]);
+      v[2 * e] += f.x;
+      v[2 * e + 1] += f.y;
+    }
+    xr[0] = make_float4(v[0], v[1], v[2], v[3]);
+    xr[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += v[i];
@@ -64,6 +81,33 @@ layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ gam
   o.z = pack_bf16x2(v[4] * rstd * g1.x + b1.x, v[5] * rstd * g1.y + b1.y);
   o.w = pack_bf16x2(v[6] * rstd * g1.z + b1.z, v[7] * rstd * g1.w + b1.w);
   reinterpret_cast<uint4*>(y + (size_t)warp * kDim)[lane] = o;
+}
+
+// (x += delta) ; xbf = bf16(x): closes the last attention block and feeds the pooling GEMM. 8 channels per thread.
+__global__ void __launch_bounds__(256)
+add_convert_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta /*nullable*/,
+                        __nv_bfloat16* __restrict__ xbf, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  float4* xr = reinterpret_cast<float4*>(x) + 2 * i;
+  const float4 a = xr[0], b = xr[1];
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (delta) {
+    const uint4 d = reinterpret_cast<const uint4*>(delta)[i];
+    const __nv_bfloat162* dp = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(dp[e]);
+      v[2 * e] += f.x;
+      v[2 * e + 1] += f.y;
+    }
+    xr[0] = make_float4(v[0], v[1], v[2], v[3]);
+    xr[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  reinterpret_cast<uint4*>(xbf)[i] = o;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -232,7 +232,7 @@ int prep_f32(vfp_weights* w, const float* src, size_t n, float** dev) {
 constexpr int64_t kConvPassFrames = 16384;
 
 struct TokenWs {
-  size_t cu, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, h, logits, xbf, pooled, pooled_bf, head_h, total;
+  size_t cu, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, h, logits, xbf, pooled, pooled_bf, head_h, total;
 };
 struct ConvWs {
   size_t c1, c2, c3, total;
@@ -254,6 +254,7 @@ TokenWs token_ws_layout(int64_t F, int64_t C) {
   L.xn = take((size_t)F * kDim * 2);
   L.qkv = take((size_t)F * 3 * kDim * 2);
   L.att = take((size_t)F * kDim * 2);
+  L.delta = take((size_t)F * kDim * 2);
   L.h = take((size_t)F * 4 * kDim * 2);
   L.logits = take((size_t)F * kDim * 4);
   L.xbf = take((size_t)F * kDim * 2);
@@ -555,9 +556,10 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
       s.tap_w[kb] = (signed char)kConv2KBlocks[kb].dw;
       s.tap_h[kb] = (signed char)kConv2KBlocks[kb].dh;
     }
-    EpiBiasAct::Params ep{};
-    ep.bias = w->c2_b; ep.out_bf16 = c2a; ep.ld_out = 64; ep.M = (int)(F * 256); ep.N = 64; ep.act = 1;
-    VFP_CUDA((launch_gemm_bres<64, 64, 6, 6, EpiBiasAct>(ta, w->tm_c2, s, ep, st)));
+    EpiBiasActTma<true>::Params ep{};
+    if (make_tmap_out(&ep.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (conv2 out)");
+    ep.bias = w->c2_b; ep.N = 64; ep.act = 1;
+    VFP_CUDA((launch_gemm_bres<64, 64, 6, 6, EpiBiasActTma<true>>(ta, w->tm_c2, s, ep, st)));
     g_prof.mark(kStConv2, st);
   }
   {  // conv3: 16x16x64 -> 8x8x128 through a stride-2 box, tile = 2 frames
@@ -566,9 +568,10 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     s.m_tiles = (int)((F + 1) / 2); s.n_tiles = 1; s.k_blocks = 9; s.group_m = 16; s.a_conv = 1;
     s.tiles_per_frame = 1; s.frames_per_tile = 2; s.tile_out_rows = 8;
     conv_taps_strided(&s, 1);
-    EpiBiasAct::Params ep{};
-    ep.bias = w->c3_b; ep.out_bf16 = c3a; ep.ld_out = 128; ep.M = (int)(F * 64); ep.N = 128; ep.act = 1;
-    VFP_CUDA((launch_gemm_bres<128, 64, 4, 9, EpiBiasAct>(ta, w->tm_c3, s, ep, st)));
+    EpiBiasActTma<true>::Params ep{};
+    if (make_tmap_out(&ep.tmap_out, c3a, (uint64_t)F * 64, 128, true)) return fail("tensor map encode failed (conv3 out)");
+    ep.bias = w->c3_b; ep.N = 128; ep.act = 1;
+    VFP_CUDA((launch_gemm<128, 64, 6, EpiBiasActTma<true>>(ta, w->tm_c3, s, ep, st)));
     g_prof.mark(kStConv3, st);
   }
   {  // conv4: 8x8x128 -> 4x4x256 + ReLU + global average pool, tile = 8 frames
@@ -603,6 +606,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(ws + L.xn);
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws + L.qkv);
   __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws + L.att);
+  __nv_bfloat16* delta = reinterpret_cast<__nv_bfloat16*>(ws + L.delta);
   __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(ws + L.h);
   float* logits = reinterpret_cast<float*>(ws + L.logits);
   __nv_bfloat16* xbf = reinterpret_cast<__nv_bfloat16*>(ws + L.xbf);
@@ -640,6 +644,22 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     }
     return 0;
   };
+  // bf16-output token GEMM, result written by the TMA unit (coalesced); act: 0 none, 2 gelu
+  auto token_gemm_bf16 = [&](const __nv_bfloat16* A, int64_t M, int K, const CUtensorMap& tb, int N, const float* bias, int act,
+                             __nv_bfloat16* out) -> int {
+    CUtensorMap tma;
+    if (make_tmap_rows_bf16(&tma, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 64)) return fail("tensor map encode failed (tokens)");
+    EpiBiasActTma<true>::Params ep{};
+    if (make_tmap_out(&ep.tmap_out, out, (uint64_t)M, (uint64_t)N, true)) return fail("tensor map encode failed (token out)");
+    ep.bias = bias; ep.N = N; ep.act = act;
+    GemmShape s = plain_shape(M, N, K, 256, 64, 32);
+    if (K == 256) {
+      VFP_CUDA((launch_gemm_bres<256, 64, 4, 4, EpiBiasActTma<true>>(tma, tb, s, ep, st)));
+    } else {
+      VFP_CUDA((launch_gemm<256, 64, 4, EpiBiasActTma<true>>(tma, tb, s, ep, st)));
+    }
+    return 0;
+  };
   {
     EpiBiasAct::Params ep{};
     ep.bias = w->btok; ep.pe = w->pe; ep.token_pos = tok_pos; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
@@ -656,43 +676,29 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   // ---- attention blocks ----
   const unsigned ln_grid = (unsigned)((F * 32 + 255) / 256);
   const dim3 att_grid((unsigned)C, kHeads, (unsigned)((max_T + kAttQ - 1) / kAttQ));
+  // residual updates travel as bf16 `delta` and are folded into the fp32 stream by the next LayerNorm (see there)
   for (int b = 0; b < w->n_attn; ++b) {
     const AttnBlockWeights& a = w->attn[b];
-    layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, a.ln1_w, a.ln1_b, xn, (int)F);
+    add_layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, b > 0 ? delta : nullptr, a.ln1_w, a.ln1_b, xn, (int)F);
     g_prof.mark(kStLayerNorm, st);
-    {
-      EpiBiasAct::Params ep{};
-      ep.bias = a.bqkv; ep.out_bf16 = qkv; ep.ld_out = 3 * kDim; ep.M = (int)F; ep.N = 3 * kDim;
-      if (token_gemm(xn, F, kDim, a.tm_qkv, 3 * kDim, ep)) return 1;
-      g_prof.mark(kStQkv, st);
-    }
+    if (token_gemm_bf16(xn, F, kDim, a.tm_qkv, 3 * kDim, a.bqkv, 0, qkv)) return 1;
+    g_prof.mark(kStQkv, st);
     attention_mma_kernel<<<att_grid, 128, 0, st>>>(qkv, d_cu, att);
     g_prof.mark(kStAttention, st);
-    {
-      EpiBiasAct::Params ep{};
-      ep.bias = a.bo; ep.residual = xa; ep.ld_res = kDim; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
-      if (token_gemm(att, F, kDim, a.tm_o, kDim, ep)) return 1;
-      g_prof.mark(kStOutProj, st);
-    }
-    layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, a.ln2_w, a.ln2_b, xn, (int)F);
+    if (token_gemm_bf16(att, F, kDim, a.tm_o, kDim, a.bo, 0, delta)) return 1;
+    g_prof.mark(kStOutProj, st);
+    add_layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, delta, a.ln2_w, a.ln2_b, xn, (int)F);
     g_prof.mark(kStLayerNorm, st);
-    {
-      EpiBiasAct::Params ep{};
-      ep.bias = a.b1; ep.act = 2; ep.out_bf16 = hbuf; ep.ld_out = 4 * kDim; ep.M = (int)F; ep.N = 4 * kDim;
-      if (token_gemm(xn, F, kDim, a.tm_w1, 4 * kDim, ep)) return 1;
-      g_prof.mark(kStMlp1, st);
-    }
-    {
-      EpiBiasAct::Params ep{};
-      ep.bias = a.b2; ep.residual = xa; ep.ld_res = kDim; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
-      if (token_gemm(hbuf, F, 4 * kDim, a.tm_w2, kDim, ep)) return 1;
-      g_prof.mark(kStMlp2, st);
-    }
+    if (token_gemm_bf16(xn, F, kDim, a.tm_w1, 4 * kDim, a.b1, 2, hbuf)) return 1;
+    g_prof.mark(kStMlp1, st);
+    if (token_gemm_bf16(hbuf, F, 4 * kDim, a.tm_w2, kDim, a.b2, 0, delta)) return 1;
+    g_prof.mark(kStMlp2, st);
   }
+  // close the last block's residual and make the bf16 copy the pooling GEMM reads
+  add_convert_bf16_kernel<<<(unsigned)((F * kDim / 8 + 255) / 256), 256, 0, st>>>(xa, w->n_attn > 0 ? delta : nullptr, xbf, F * kDim / 8);
   if (features_out)
     VFP_CUDA(cudaMemcpyAsync(features_out + (size_t)f0 * kDim, xa, (size_t)F * kDim * 4, cudaMemcpyDeviceToDevice, st));
   // ---- pooling + head ----
-  f32_to_bf16_kernel<<<(unsigned)((F * kDim / 8 + 255) / 256), 256, 0, st>>>(xa, xbf, F * kDim / 8);
   {
     EpiBiasAct::Params ep{};
     ep.bias = w->bpool; ep.act = 1; ep.out_f32 = logits; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
