@@ -179,6 +179,48 @@ static int run_conv(int frames) {
   return ok ? 0 : 1;
 }
 
+template <int BN, int BK, int ST, int MTILES>
+static int run_plain_mt(long long M, int N, int K) {
+  std::vector<__nv_bfloat16> hA(M * K), hB((size_t)N * K);
+  std::vector<float> hbias(N);
+  for (auto& v : hA) v = f2b(frand());
+  for (auto& v : hB) v = f2b(frand());
+  for (auto& v : hbias) v = frand();
+  __nv_bfloat16 *dA, *dB, *dO;
+  float* dbias;
+  CK(cudaMalloc(&dA, hA.size() * 2));
+  CK(cudaMalloc(&dB, hB.size() * 2));
+  CK(cudaMalloc(&dbias, N * 4));
+  CK(cudaMalloc(&dO, M * N * 2));
+  CK(cudaMemcpy(dA, hA.data(), hA.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, hB.data(), hB.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias, hbias.data(), N * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(dO, 0xFF, M * N * 2));
+  CUtensorMap ta, tb;
+  if (make_tmap_rows_bf16(&ta, dA, M, K, K, 128, BK) || make_tmap_rows_bf16(&tb, dB, N, K, K, BN, BK)) return 1;
+  GemmShape s = plain_shape(M, N, K, BN, BK, 4);
+  EpiBiasActTma<true>::Params ep{};
+  if (make_tmap_out(&ep.tmap_out, dO, M, N, true)) return 1;
+  ep.bias = dbias; ep.N = N; ep.act = 1;
+  CK((launch_gemm<BN, BK, ST, EpiBiasActTma<true>, MTILES>(ta, tb, s, ep, 0)));
+  CK(cudaDeviceSynchronize());
+  std::vector<__nv_bfloat16> hO(M * N);
+  CK(cudaMemcpy(hO.data(), dO, hO.size() * 2, cudaMemcpyDeviceToHost));
+  double max_err = 0;
+  for (long long m = 0; m < M; m += 3)
+    for (int n = 0; n < N; ++n) {
+      double acc = hbias[n];
+      for (int k = 0; k < K; ++k) acc += (double)b2f(hA[m * K + k]) * (double)b2f(hB[(size_t)n * K + k]);
+      if (acc < 0) acc = 0;
+      const double e = fabs(acc - b2f(hO[m * N + n])) / (1.0 + fabs(acc));
+      if (!(e <= max_err)) max_err = e;
+    }
+  const bool ok = max_err < 1e-2;
+  printf("[multi-acc MT=%d BN=%d, TMA-store bf16] M=%lld N=%d K=%d  rel_err=%.3e  %s\n", MTILES, BN, M, N, K, max_err, ok ? "OK" : "FAIL");
+  cudaFree(dA); cudaFree(dB); cudaFree(dbias); cudaFree(dO);
+  return ok ? 0 : 1;
+}
+
 template <int BN, int BK, int ST, int KBLOCKS>
 static int run_bres(long long M, int N) {
   const int K = KBLOCKS * BK;
@@ -220,8 +262,122 @@ static int run_bres(long long M, int N) {
   return ok ? 0 : 1;
 }
 
-int main() {
+// ---- micro-benchmarks (run with any argument): operand-fill behaviour of the conv2 shape ----
+struct EpiNull : EpiDefaults {
+  struct Params { int dummy; };
+  __device__ __forceinline__ void begin(const Params&, int, int, int) {}
+  __device__ __forceinline__ void end(const Params&, int, int, int) {}
+  __device__ __forceinline__ void chunk(const Params&, int, int, int, uint32_t (&)[32], int) {}
+};
+
+template <class F>
+static float time_ms(F f, int reps = 5) {
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  f();
+  cudaEventRecord(a);
+  for (int i = 0; i < reps; ++i) f();
+  cudaEventRecord(b);
+  cudaEventSynchronize(b);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms / reps;
+}
+
+static void perf() {
+  const int frames = 16384;
+  __nv_bfloat16 *c1, *w;
+  CK(cudaMalloc(&c1, (size_t)frames * 65536));
+  CK(cudaMalloc(&w, 256 * 1152 * 2));
+  CK(cudaMemset(c1, 0, (size_t)frames * 65536));
+  CK(cudaMemset(w, 0, 256 * 1152 * 2));
+  EpiNull::Params ep{0};
+  CUtensorMap ta, tb;
+  // (1) conv2 as shipped: s2d 4-D box (64 ch x 16 W x 8 H), 6 K blocks, weights resident
+  {
+    make_tmap_nhwc_bf16(&ta, c1, frames, 16, 16, 128, 64, 16, 8, 1, 1);
+    make_tmap_rows_bf16(&tb, w, 64, 384, 384, 64, 64);
+    GemmShape s{};
+    s.m_tiles = 2 * frames; s.n_tiles = 1; s.k_blocks = 6; s.group_m = 16; s.a_conv = 1; s.tiles_per_frame = 2; s.frames_per_tile = 1;
+    s.tile_out_rows = 8; s.h_mul = 1;
+    const int c[6] = {1, 0, 1, 1, 0, 1}, dw[6] = {0, 0, 0, -1, -1, -1}, dh[6] = {-1, 0, 0, -1, 0, 0};
+    for (int k = 0; k < 6; ++k) { s.tap_c_blk[k] = c[k]; s.tap_w[k] = dw[k]; s.tap_h[k] = dh[k]; }
+    printf("conv2 s2d 4-D box, B resident      : %.3f ms\n", time_ms([&] { launch_gemm_bres<64, 64, 6, 6, EpiNull>(ta, tb, s, ep, 0); }));
+    for (int k = 0; k < 6; ++k) { s.tap_w[k] = 0; s.tap_h[k] = 0; }
+    printf("  same, all taps at offset 0 (L2 re-use): %.3f ms\n", time_ms([&] { launch_gemm_bres<64, 64, 6, 6, EpiNull>(ta, tb, s, ep, 0); }));
+  }
+  // (2) same bytes as a plain 2-D matrix [frames*256][384] (rows of 768 B, box 128 x 128 B)
+  {
+    const long long M2 = (long long)frames * 65536 / 768;  // same bytes as c1
+    make_tmap_rows_bf16(&ta, c1, (uint64_t)M2, 384, 384, 128, 64);
+    make_tmap_rows_bf16(&tb, w, 64, 384, 384, 64, 64);
+    GemmShape s = plain_shape(M2, 64, 384, 64, 64, 16);
+    printf("(plain 2-D has %.2fx the row tiles of conv2)\n", (double)s.m_tiles / (2.0 * frames));
+    printf("plain 2-D [M][384] N=64, B resident : %.3f ms\n", time_ms([&] { launch_gemm_bres<64, 64, 6, 6, EpiNull>(ta, tb, s, ep, 0); }));
+    printf("plain 2-D [M][384] N=64, generic    : %.3f ms\n", time_ms([&] { launch_gemm<64, 64, 8, EpiNull>(ta, tb, s, ep, 0); }));
+    printf("plain 2-D [M][384] N=64, generic MT=2: %.3f ms\n", time_ms([&] { launch_gemm<64, 64, 4, EpiNull, 2>(ta, tb, s, ep, 0); }));
+    printf("plain 2-D [M][384] N=64, generic MT=3: %.3f ms\n", time_ms([&] { launch_gemm<64, 64, 3, EpiNull, 3>(ta, tb, s, ep, 0); }));
+    printf("plain 2-D [M][384] N=64, generic MT=4: %.3f ms\n", time_ms([&] { launch_gemm<64, 64, 2, EpiNull, 4>(ta, tb, s, ep, 0); }));
+  }
+  // (2b) L2-resident operand (50 MB): isolates the MMA/TMEM side from HBM
+  {
+    const long long M3 = 65536;
+    make_tmap_rows_bf16(&ta, c1, (uint64_t)M3, 384, 384, 128, 64);
+    make_tmap_rows_bf16(&tb, w, 64, 384, 384, 64, 64);
+    GemmShape s = plain_shape(M3, 64, 384, 64, 64, 16);
+    const double fl = 2.0 * M3 * 64 * 384 / 1e9;
+    float t;
+    t = time_ms([&] { launch_gemm<64, 64, 8, EpiNull>(ta, tb, s, ep, 0); }, 20); printf("L2-resident N=64 K=384 MT=1: %.4f ms %.0f TFLOP/s\n", t, fl / t);
+    t = time_ms([&] { launch_gemm<64, 64, 4, EpiNull, 2>(ta, tb, s, ep, 0); }, 20); printf("L2-resident N=64 K=384 MT=2: %.4f ms %.0f TFLOP/s\n", t, fl / t);
+    t = time_ms([&] { launch_gemm<64, 64, 3, EpiNull, 3>(ta, tb, s, ep, 0); }, 20); printf("L2-resident N=64 K=384 MT=3: %.4f ms %.0f TFLOP/s\n", t, fl / t);
+    t = time_ms([&] { launch_gemm<64, 64, 2, EpiNull, 4>(ta, tb, s, ep, 0); }, 20); printf("L2-resident N=64 K=384 MT=4: %.4f ms %.0f TFLOP/s\n", t, fl / t);
+    make_tmap_rows_bf16(&ta, c1, (uint64_t)M3, 576, 576, 128, 64);
+    make_tmap_rows_bf16(&tb, w, 128, 576, 576, 128, 64);
+    GemmShape s3 = plain_shape(M3, 128, 576, 128, 64, 16);
+    const double fl3 = 2.0 * M3 * 128 * 576 / 1e9;
+    t = time_ms([&] { launch_gemm<128, 64, 6, EpiNull>(ta, tb, s3, ep, 0); }, 20); printf("L2-resident N=128 K=576 MT=1: %.4f ms %.0f TFLOP/s\n", t, fl3 / t);
+    t = time_ms([&] { launch_gemm<128, 64, 4, EpiNull, 2>(ta, tb, s3, ep, 0); }, 20); printf("L2-resident N=128 K=576 MT=2: %.4f ms %.0f TFLOP/s\n", t, fl3 / t);
+    make_tmap_rows_bf16(&ta, c1, (uint64_t)M3, 1152, 1152, 128, 64);
+    make_tmap_rows_bf16(&tb, w, 256, 1152, 1152, 256, 64);
+    GemmShape s4 = plain_shape(M3 / 2, 256, 1152, 256, 64, 16);
+    const double fl4 = 2.0 * (M3 / 2) * 256 * 1152 / 1e9;
+    t = time_ms([&] { launch_gemm<256, 64, 4, EpiNull>(ta, tb, s4, ep, 0); }, 20); printf("L2-resident N=256 K=1152 MT=1: %.4f ms %.0f TFLOP/s\n", t, fl4 / t);
+  }
+  // (2c) conv2 4-D s2d box on an L2-resident set of frames (512 frames = 32 MB), MT sweep
+  {
+    const int f2 = 512;
+    make_tmap_nhwc_bf16(&ta, c1, f2, 16, 16, 128, 64, 16, 8, 1, 1);
+    make_tmap_rows_bf16(&tb, w, 64, 384, 384, 64, 64);
+    GemmShape s{};
+    s.m_tiles = 2 * f2; s.n_tiles = 1; s.k_blocks = 6; s.group_m = 16; s.a_conv = 1; s.tiles_per_frame = 2; s.frames_per_tile = 1;
+    s.tile_out_rows = 8; s.h_mul = 1; s.n_segments = 1;
+    const int c[6] = {1, 0, 1, 1, 0, 1}, dw[6] = {0, 0, 0, -1, -1, -1}, dh[6] = {-1, 0, 0, -1, 0, 0};
+    for (int k = 0; k < 6; ++k) { s.tap_c_blk[k] = c[k]; s.tap_w[k] = dw[k]; s.tap_h[k] = dh[k]; }
+    const double fl = 2.0 * f2 * 256 * 64 * 384 / 1e9;
+    float t;
+    t = time_ms([&] { launch_gemm<64, 64, 8, EpiNull>(ta, tb, s, ep, 0); }, 20); printf("conv2 4-D box, 512 frames MT=1: %.4f ms %.0f TFLOP/s\n", t, fl / t);
+    t = time_ms([&] { launch_gemm<64, 64, 3, EpiNull, 3>(ta, tb, s, ep, 0); }, 20); printf("conv2 4-D box, 512 frames MT=3: %.4f ms %.0f TFLOP/s\n", t, fl / t);
+  }
+  // (3) N = 256, K = 256 token GEMM shape on the same buffer: [M][256]
+  {
+    const long long M = 1 << 20;  // 512 MB of the 1 GB buffer
+    make_tmap_rows_bf16(&ta, c1, M, 256, 256, 128, 64);
+    make_tmap_rows_bf16(&tb, w, 256, 256, 256, 256, 64);
+    GemmShape s = plain_shape(M, 256, 256, 256, 64, 16);
+    const float t1 = time_ms([&] { launch_gemm_bres<256, 64, 4, 4, EpiNull>(ta, tb, s, ep, 0); });
+    const float t2 = time_ms([&] { launch_gemm<256, 64, 4, EpiNull>(ta, tb, s, ep, 0); });
+    printf("token GEMM M=1M N=256 K=256: B resident %.3f ms (%.0f TFLOP/s), generic %.3f ms (%.0f TFLOP/s)\n", t1,
+           2.0 * M * 256 * 256 / t1 / 1e9, t2, 2.0 * M * 256 * 256 / t2 / 1e9);
+  }
+  CK(cudaDeviceSynchronize());
+  cudaFree(c1); cudaFree(w);
+}
+
+int main(int argc, char**) {
+  if (argc > 1) { perf(); return 0; }
   int fails = 0;
+  fails += run_plain_mt<64, 64, 3, 3>(5000, 64, 384);
+  fails += run_plain_mt<128, 64, 4, 2>(3333, 128, 576);
   fails += run_bres<256, 64, 4, 4>(300, 256);
   fails += run_bres<256, 64, 4, 4>(40000, 768);     // several column tiles per CTA: B is reloaded mid-range
   fails += run_bres<256, 64, 4, 4>(128 * 200, 1024);

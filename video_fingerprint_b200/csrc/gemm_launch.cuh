@@ -17,20 +17,21 @@ inline int device_sm_count() {
   return sms;
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, class Epi>
+template <int BLOCK_N, int BLOCK_K, int STAGES, class Epi, int MT = 1>
 inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& shape,
                                const typename Epi::Params& ep, cudaStream_t stream) {
-  using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES>;
+  using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES, MT>;
   constexpr int kSmem = L::kTotal + Epi::kExtraSmemBytes;
   static_assert(kSmem <= 232448, "shared memory budget");
-  auto kernel = gemm_tcgen05_kernel<BLOCK_N, BLOCK_K, STAGES, Epi>;
+  auto kernel = gemm_tcgen05_kernel<BLOCK_N, BLOCK_K, STAGES, Epi, MT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const int total = shape.row_resident ? shape.m_tiles * shape.n_segments : shape.m_tiles * shape.n_tiles;
+  const int m_super = (shape.m_tiles + MT - 1) / MT;
+  const int total = shape.row_resident ? m_super * shape.n_segments : m_super * shape.n_tiles;
   if (total <= 0) return cudaSuccess;
   const int grid = total < device_sm_count() ? total : device_sm_count();
   kernel<<<grid, gemm_threads<BLOCK_N, Epi>(), kSmem, stream>>>(ta, tb, shape, ep);

@@ -96,32 +96,39 @@ struct TileWalk {
   }
 };
 
-template <int BLOCK_N, int BLOCK_K, int STAGES>
+template <int BLOCK_N, int BLOCK_K, int STAGES, int MT = 1>
 struct GemmSmemLayout {
   static constexpr int kRowBytes = BLOCK_K * 2;
-  static constexpr int kABytes = kBlockM * kRowBytes;
+  static constexpr int kABytes = kBlockM * kRowBytes;      // one 128-row sub-tile of A
+  static constexpr int kAStage = MT * kABytes;
   static constexpr int kBBytes = BLOCK_N * kRowBytes;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = kAStage + kBBytes;
   static constexpr int kBarrierBytes = 256;
   static constexpr int kCore = STAGES * kStageBytes + kBarrierBytes;
   static constexpr int kCoreAligned = (kCore + 1023) / 1024 * 1024;  // epilogue staging starts 1024-aligned
   static constexpr int kTotal = kCoreAligned + 1024 /*alignment slack*/;
 };
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, class Epilogue>
+// MT > 1: one CTA tile = MT consecutive 128-row sub-tiles sharing the B tile, each with its own TMEM accumulator.
+// UMMAs that accumulate into the SAME TMEM tile issue back to back only every ~180 cycles (measured: 24 dependent
+// M128 N64 K16 instructions take 4300 cycles), which starves narrow tiles (N=64: 32 cycles of work per
+// instruction). Round-robin over MT independent accumulators hides that latency.
+template <int BLOCK_N, int BLOCK_K, int STAGES, class Epilogue, int MT = 1>
 __global__ void __launch_bounds__(gemm_threads<BLOCK_N, Epilogue>(), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmShape shape, const __grid_constant__ typename Epilogue::Params ep) {
-  using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES>;
+                    const GemmShape shape_in, const __grid_constant__ typename Epilogue::Params ep) {
+  using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES, MT>;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32 || BLOCK_K == 16, "BLOCK_K");
-  constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
-                                 : (2 * BLOCK_N <= 256) ? 256 : 512;
+  static_assert(2 * MT * BLOCK_N <= 512, "TMEM: two buffers of MT accumulators");
+  constexpr int kAccCols = MT * BLOCK_N;  // columns of one accumulator buffer
+  constexpr uint32_t kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
+                                 : (2 * kAccCols <= 256) ? 256 : 512;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * L::kABytes;
+  uint8_t* smem_b = smem + STAGES * L::kAStage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
   uint64_t* full_bar = bars;                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]
@@ -131,6 +138,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // the tile walk runs over super-tiles of MT row tiles
+  GemmShape shape = shape_in;
+  const int m_tiles_real = shape_in.m_tiles;
+  shape.m_tiles = (shape_in.m_tiles + MT - 1) / MT;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -160,26 +171,36 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       TileWalk walk(shape, blockIdx.x, gridDim.x);
-      int mt, nt;
+      int mts, nt;
       bool first, last;
-      while (walk.next(mt, nt, first, last)) {
-        int frame0 = 0, oh0 = 0;
-        if (shape.a_conv) {
-          if (shape.tiles_per_frame > 1) {
-            frame0 = mt / shape.tiles_per_frame;
-            oh0 = (mt - frame0 * shape.tiles_per_frame) * shape.tile_out_rows;
-          } else {
-            frame0 = mt * shape.frames_per_tile;
+      while (walk.next(mts, nt, first, last)) {
+        int frame0[MT], oh0[MT];
+#pragma unroll
+        for (int sub = 0; sub < MT; ++sub) {
+          const int mt = mts * MT + sub;
+          frame0[sub] = 0;
+          oh0[sub] = 0;
+          if (shape.a_conv) {
+            if (shape.tiles_per_frame > 1) {
+              frame0[sub] = mt / shape.tiles_per_frame;
+              oh0[sub] = (mt - frame0[sub] * shape.tiles_per_frame) * shape.tile_out_rows;
+            } else {
+              frame0[sub] = mt * shape.frames_per_tile;
+            }
           }
         }
         for (int kb = 0; kb < shape.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-          if (shape.a_conv) {
-            tma_load_4d(&tmap_a, &full_bar[stage], smem_a + stage * L::kABytes, shape.tap_c_blk[kb] * BLOCK_K,
-                        shape.tap_w[kb], shape.h_mul * oh0 + shape.tap_h[kb], frame0);
-          } else {
-            tma_load_2d(&tmap_a, &full_bar[stage], smem_a + stage * L::kABytes, kb * BLOCK_K, mt * kBlockM);
+#pragma unroll
+          for (int sub = 0; sub < MT; ++sub) {
+            uint8_t* dst = smem_a + stage * L::kAStage + sub * L::kABytes;
+            if (shape.a_conv) {
+              tma_load_4d(&tmap_a, &full_bar[stage], dst, shape.tap_c_blk[kb] * BLOCK_K, shape.tap_w[kb],
+                          shape.h_mul * oh0[sub] + shape.tap_h[kb], frame0[sub]);
+            } else {
+              tma_load_2d(&tmap_a, &full_bar[stage], dst, kb * BLOCK_K, (mts * MT + sub) * kBlockM);
+            }
           }
           tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * L::kBBytes, kb * BLOCK_K, nt * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -194,23 +215,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       uint32_t phase = 0;
       int local = 0;
       TileWalk walk(shape, blockIdx.x, gridDim.x);
-      int mt, nt;
+      int mts, nt;
       bool first, last;
-      for (; walk.next(mt, nt, first, last); ++local) {
+      for (; walk.next(mts, nt, first, last); ++local) {
         const int acc = local & 1;
         const uint32_t acc_phase = (local >> 1) & 1;
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * kAccCols;
         for (int kb = 0; kb < shape.k_blocks; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_smem_desc_kmajor<L::kRowBytes>(smem_u32(smem_a + stage * L::kABytes));
           const uint64_t bdesc = umma_smem_desc_kmajor<L::kRowBytes>(smem_u32(smem_b + stage * L::kBBytes));
+          const uint32_t a_base = smem_u32(smem_a + stage * L::kAStage);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
-            // advancing 16 bf16 along K = 32 bytes = 2 units of the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub) {
+              // advancing 16 bf16 along K = 32 bytes = 2 units of the (addr >> 4) field
+              const uint64_t adesc = umma_smem_desc_kmajor<L::kRowBytes>(a_base + sub * L::kABytes);
+              umma_bf16(d_tmem + sub * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -227,34 +252,39 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
     int local = 0;
     TileWalk walk(shape, blockIdx.x, gridDim.x);
-    int mt, nt;
+    int mts, nt;
     bool first, last;
     Epilogue epi;
     uint8_t* extra_smem = smem + L::kCoreAligned;
     epi.setup(ep, extra_smem, warp - 2, lane);
-    for (; walk.next(mt, nt, first, last); ++local) {
+    for (; walk.next(mts, nt, first, last); ++local) {
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
-      if (first) epi.item_begin(ep, mt, walk.seg, row, extra_smem);
+      if (first) epi.item_begin(ep, mts, walk.seg, row, extra_smem);
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
-      epi.begin(ep, mt, nt, row);
 #pragma unroll 1
-      for (int pass = 0; pass < Epilogue::kPasses; ++pass) {  // row-wise reductions re-read the accumulator
+      for (int sub = 0; sub < MT; ++sub) {
+        const int mt = mts * MT + sub;
+        if (mt >= m_tiles_real) break;  // warp-uniform
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols + sub * BLOCK_N;
+        epi.begin(ep, mt, nt, row);
 #pragma unroll 1
-        for (int c = col_begin; c < col_begin + kColsPerWarp; c += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c, v);
-          tmem_ld_wait();
-          epi.chunk(ep, mt, nt * BLOCK_N + c, row, v, pass);
+        for (int pass = 0; pass < Epilogue::kPasses; ++pass) {  // row-wise reductions re-read the accumulator
+#pragma unroll 1
+          for (int c = col_begin; c < col_begin + kColsPerWarp; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c, v);
+            tmem_ld_wait();
+            epi.chunk(ep, mt, nt * BLOCK_N + c, row, v, pass);
+          }
         }
+        epi.end(ep, mt, nt, row);
       }
-      epi.end(ep, mt, nt, row);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (last) epi.item_end(ep, mt, walk.seg, row, extra_smem);
+      if (last) epi.item_end(ep, mts, walk.seg, row, extra_smem);
     }
     epi.finish(ep, lane);
   }

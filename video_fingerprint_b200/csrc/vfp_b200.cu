@@ -559,7 +559,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     EpiBiasActTma<true>::Params ep{};
     if (make_tmap_out(&ep.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (conv2 out)");
     ep.bias = w->c2_b; ep.N = 64; ep.act = 1;
-    VFP_CUDA((launch_gemm_bres<64, 64, 6, 6, EpiBiasActTma<true>>(ta, w->tm_c2, s, ep, st)));
+    VFP_CUDA((launch_gemm<64, 64, 3, EpiBiasActTma<true>, 3>(ta, w->tm_c2, s, ep, st)));
     g_prof.mark(kStConv2, st);
   }
   {  // conv3: 16x16x64 -> 8x8x128 through a stride-2 box, tile = 2 frames
@@ -571,7 +571,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     EpiBiasActTma<true>::Params ep{};
     if (make_tmap_out(&ep.tmap_out, c3a, (uint64_t)F * 64, 128, true)) return fail("tensor map encode failed (conv3 out)");
     ep.bias = w->c3_b; ep.N = 128; ep.act = 1;
-    VFP_CUDA((launch_gemm<128, 64, 6, EpiBiasActTma<true>>(ta, w->tm_c3, s, ep, st)));
+    VFP_CUDA((launch_gemm<128, 64, 4, EpiBiasActTma<true>, 2>(ta, w->tm_c3, s, ep, st)));
     g_prof.mark(kStConv3, st);
   }
   {  // conv4: 8x8x128 -> 4x4x256 + ReLU + global average pool, tile = 8 frames
