@@ -12,10 +12,12 @@
 
 namespace vfp {
 
-constexpr int kC1Threads = 256;
+constexpr int kC1Threads = 128;   // 4 warps; small CTAs so ~5 frames are in flight per SM
 constexpr int kC1PadW = 68;   // columns -2 .. 65
 constexpr int kC1PadH = 67;   // rows    -2 .. 64
 constexpr int kC1SmemElems = kC1PadH * kC1PadW * 3 + 8;
+constexpr int kC1CellPitch = 272;                 // 256 B cell + 16 B pad: conflict-free fragment stores
+constexpr int kC1StageBytes = 8 * kC1CellPitch;   // per warp: 8 cells
 
 enum FrameDtype : int { kFrameU8 = 0, kFrameBF16 = 1, kFrameF32 = 2 };
 
@@ -32,6 +34,7 @@ conv1_stem_kernel(const void* __restrict__ frames, int frame_dtype, long long n_
                   const uint32_t* __restrict__ wpack, const float* __restrict__ bias,
                   __nv_bfloat16* __restrict__ out) {
   __shared__ __align__(16) __nv_bfloat16 tile[kC1SmemElems];
+  __shared__ __align__(16) uint8_t stage[(kC1Threads / 32) * kC1StageBytes];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, tig = lane & 3;
@@ -95,46 +98,61 @@ conv1_stem_kernel(const void* __restrict__ frames, int frame_dtype, long long n_
     }
     __syncthreads();
 
-    // ---- 64 m-tiles of 16 pixels; warp w takes m-tiles w, w+8, ... ----
+    // ---- 64 m-tiles of 16 pixels, processed as 32 vertical PAIRS (output rows 2j, 2j+1; same 16 columns): in the
+    //      space-to-depth output a pair covers 8 whole cells = 2 KB of contiguous global memory. The fragments are
+    //      re-assembled through a padded per-warp staging tile so that the global stores are full 512-byte lines
+    //      (direct fragment stores put 8 different lines into every store instruction: ncu showed the LSU, not HBM or
+    //      the tensor pipe, as the limiter of this kernel). ----
     const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
     __nv_bfloat16* out_f = out + f * (1024 * 32);
-#pragma unroll 2
-    for (int mt = warp; mt < 64; mt += 8) {
-      const int oh = mt >> 1;
-      const int ow0 = (mt & 1) * 16;
-      float acc[4][4];
+    uint8_t* my_stage = stage + warp * kC1StageBytes;
+#pragma unroll 1
+    for (int pair = warp; pair < 32; pair += kC1Threads / 32) {
+      const int j = pair >> 1;            // output rows 2j, 2j+1 = cell row j
+      const int ow0 = (pair & 1) * 16;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+      for (int sh = 0; sh < 2; ++sh) {
+        const int oh = 2 * j + sh;
+        float acc[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
+        for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int kh = 0; kh < 5; ++kh) {
-        // element offset of (pixel ow, k) = ((2*oh+kh)*PadW + 2*ow)*3 + k ; all terms even -> word aligned
-        const int base_lo = (((2 * oh + kh) * kC1PadW + 2 * (ow0 + g)) * 3) >> 1;
-        const int base_hi = base_lo + 24;  // pixel +8 -> +16 columns -> +48 elements -> +24 words
-        uint32_t a[4];
-        a[0] = tile32[base_lo + tig];
-        a[1] = tile32[base_hi + tig];
-        a[2] = tile32[base_lo + tig + 4];
-        a[3] = tile32[base_hi + tig + 4];
+          for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a, bfrag[kh][nt]);
+        for (int kh = 0; kh < 5; ++kh) {
+          // element offset of (pixel ow, k) = ((2*oh+kh)*PadW + 2*ow)*3 + k ; all terms even -> word aligned
+          const int base_lo = (((2 * oh + kh) * kC1PadW + 2 * (ow0 + g)) * 3) >> 1;
+          const int base_hi = base_lo + 24;  // pixel +8 -> +16 columns -> +48 elements -> +24 words
+          uint32_t a[4];
+          a[0] = tile32[base_lo + tig];
+          a[1] = tile32[base_hi + tig];
+          a[2] = tile32[base_lo + tig + 4];
+          a[3] = tile32[base_hi + tig + 4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a, bfrag[kh][nt]);
+        }
+        // pixel ow0+g -> cell g/2, sub-position sh*2 + g%2; pixel +8 -> cell +4. Cells are 272 B apart in staging.
+        uint8_t* p_lo = my_stage + (g >> 1) * kC1CellPitch + (sh * 2 + (g & 1)) * 64 + 4 * tig;
+        uint8_t* p_hi = p_lo + 4 * kC1CellPitch;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float v0 = fmaxf(acc[nt][0] + bia[nt][0], 0.0f);
+          const float v1 = fmaxf(acc[nt][1] + bia[nt][1], 0.0f);
+          const float v2 = fmaxf(acc[nt][2] + bia[nt][0], 0.0f);
+          const float v3 = fmaxf(acc[nt][3] + bia[nt][1], 0.0f);
+          *reinterpret_cast<__nv_bfloat162*>(p_lo + nt * 16) = __floats2bfloat162_rn(v0, v1);
+          *reinterpret_cast<__nv_bfloat162*>(p_hi + nt * 16) = __floats2bfloat162_rn(v2, v3);
+        }
       }
-      // space-to-depth store: pixel (oh, ow) -> cell (oh/2, ow/2), channel block (oh%2)*2 + ow%2; conv2 then reads
-      // dense channel slices instead of every second pixel. Pixel +8 along W = cell +4 = +512 elements.
-      const int ow = ow0 + g;
-      const int p_lo = ((oh >> 1) * 16 + (ow >> 1)) * 4 + (oh & 1) * 2 + (ow & 1);
+      __syncwarp();
+      // 8 cells x 256 B = 128 chunks of 16 B, contiguous in global memory
+      uint4* dst = reinterpret_cast<uint4*>(out_f + ((size_t)j * 16 + (ow0 >> 1)) * 128);
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const float v0 = fmaxf(acc[nt][0] + bia[nt][0], 0.0f);
-        const float v1 = fmaxf(acc[nt][1] + bia[nt][1], 0.0f);
-        const float v2 = fmaxf(acc[nt][2] + bia[nt][0], 0.0f);
-        const float v3 = fmaxf(acc[nt][3] + bia[nt][1], 0.0f);
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v0, v1);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(v2, v3);
-        *reinterpret_cast<__nv_bfloat162*>(out_f + p_lo * 32 + nt * 8 + 2 * tig) = lo;
-        *reinterpret_cast<__nv_bfloat162*>(out_f + (p_lo + 16) * 32 + nt * 8 + 2 * tig) = hi;
+      for (int it = 0; it < 4; ++it) {
+        const int q = it * 32 + lane;
+        dst[q] = *reinterpret_cast<const uint4*>(my_stage + (q >> 4) * kC1CellPitch + (q & 15) * 16);
       }
+      __syncwarp();
     }
     __syncthreads();  // before the next frame overwrites the tile
   }

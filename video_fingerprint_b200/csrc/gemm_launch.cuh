@@ -17,13 +17,13 @@ inline int device_sm_count() {
   return sms;
 }
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, class Epi, int MT = 1>
+template <int BLOCK_N, int BLOCK_K, int STAGES, class Epi, int MT = 1, bool SWAP = false>
 inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& shape,
                                const typename Epi::Params& ep, cudaStream_t stream) {
   using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES, MT>;
   constexpr int kSmem = L::kTotal + Epi::kExtraSmemBytes;
   static_assert(kSmem <= 232448, "shared memory budget");
-  auto kernel = gemm_tcgen05_kernel<BLOCK_N, BLOCK_K, STAGES, Epi, MT>;
+  auto kernel = gemm_tcgen05_kernel<BLOCK_N, BLOCK_K, STAGES, Epi, MT, SWAP>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);

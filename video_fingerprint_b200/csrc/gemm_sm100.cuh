@@ -113,15 +113,24 @@ struct GemmSmemLayout {
 // UMMAs that accumulate into the SAME TMEM tile issue back to back only every ~180 cycles (measured: 24 dependent
 // M128 N64 K16 instructions take 4300 cycles), which starves narrow tiles (N=64: 32 cycles of work per
 // instruction). Round-robin over MT independent accumulators hides that latency.
-template <int BLOCK_N, int BLOCK_K, int STAGES, class Epilogue, int MT = 1>
+//
+// SWAP: the roles of the two shared-memory tiles are exchanged in the UMMA: the B-region tile (weights, 128 rows =
+// output channels, rows past C_out zero-filled by TMA) becomes the M operand and the MT x 128 activation rows become
+// the N operand (N = 256 for MT = 2). An SS-mode UMMA costs ~128 cycles however narrow N is (the 128 x 16 A slice is
+// streamed from shared memory), so a conv with C_out = 64 / 128 as the N dimension uses only 25 % / 50 % of the
+// tensor pipe; with the channels on M and 256 pixels on N it is 50 % / 100 %. The accumulator then holds
+// [channel][pixel] and the epilogue transposes while staging for the TMA store.
+template <int BLOCK_N, int BLOCK_K, int STAGES, class Epilogue, int MT = 1, bool SWAP = false>
 __global__ void __launch_bounds__(gemm_threads<BLOCK_N, Epilogue>(), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmShape shape_in, const __grid_constant__ typename Epilogue::Params ep) {
   using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES, MT>;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32 || BLOCK_K == 16, "BLOCK_K");
-  static_assert(2 * MT * BLOCK_N <= 512, "TMEM: two buffers of MT accumulators");
-  constexpr int kAccCols = MT * BLOCK_N;  // columns of one accumulator buffer
+  static_assert(SWAP ? (BLOCK_N == 128 && MT * 128 <= 256) : (2 * MT * BLOCK_N <= 512), "TMEM: two accumulator buffers");
+  constexpr int kAccCols = SWAP ? MT * kBlockM : MT * BLOCK_N;  // columns of one accumulator buffer
+  constexpr int kEpiTiles = SWAP ? 1 : MT;                      // accumulator tiles the epilogue walks per CTA tile
+  constexpr int kEpiCols = SWAP ? MT * kBlockM : BLOCK_N;       // columns of one such tile
   constexpr uint32_t kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64) ? 64 : (2 * kAccCols <= 128) ? 128
                                  : (2 * kAccCols <= 256) ? 256 : 512;
 
@@ -210,7 +219,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else if (warp == 1) {
     // ------------------------------ UMMA issuer ------------------------------
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+      constexpr uint32_t idesc = SWAP ? umma_idesc_bf16(kBlockM, MT * kBlockM) : umma_idesc_bf16(kBlockM, BLOCK_N);
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
@@ -230,11 +239,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           const uint32_t a_base = smem_u32(smem_a + stage * L::kAStage);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
+            // advancing 16 bf16 along K = 32 bytes = 2 units of the (addr >> 4) field
+            if constexpr (SWAP) {
+              const uint64_t pxdesc = umma_smem_desc_kmajor<L::kRowBytes>(a_base);  // MT*128 activation rows = N
+              umma_bf16(d_tmem, bdesc + 2 * k, pxdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            } else {
 #pragma unroll
-            for (int sub = 0; sub < MT; ++sub) {
-              // advancing 16 bf16 along K = 32 bytes = 2 units of the (addr >> 4) field
-              const uint64_t adesc = umma_smem_desc_kmajor<L::kRowBytes>(a_base + sub * L::kABytes);
-              umma_bf16(d_tmem + sub * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int sub = 0; sub < MT; ++sub) {
+                const uint64_t adesc = umma_smem_desc_kmajor<L::kRowBytes>(a_base + sub * L::kABytes);
+                umma_bf16(d_tmem + sub * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
             }
           }
           umma_commit(&empty_bar[stage]);
@@ -246,7 +260,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   } else {
     // ------------------------------ epilogue ------------------------------
     constexpr int kSplit = gemm_column_split<BLOCK_N, Epilogue>();
-    constexpr int kColsPerWarp = BLOCK_N / kSplit;
+    constexpr int kColsPerWarp = kEpiCols / kSplit;
     const int quarter = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = quarter * 32 + lane;
     const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
@@ -264,9 +278,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int sub = 0; sub < MT; ++sub) {
-        const int mt = mts * MT + sub;
-        if (mt >= m_tiles_real) break;  // warp-uniform
+      for (int sub = 0; sub < kEpiTiles; ++sub) {
+        const int mt = SWAP ? mts : mts * MT + sub;  // SWAP: the epilogue sees the super-tile (MT*128 pixel columns)
+        if (!SWAP && mt >= m_tiles_real) break;      // warp-uniform
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols + sub * BLOCK_N;
         epi.begin(ep, mt, nt, row);
 #pragma unroll 1
@@ -276,7 +290,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
             uint32_t v[32];
             tmem_ld_32x32(taddr + c, v);
             tmem_ld_wait();
-            epi.chunk(ep, mt, nt * BLOCK_N + c, row, v, pass);
+            epi.chunk(ep, mt, SWAP ? c : nt * BLOCK_N + c, row, v, pass);
           }
         }
         epi.end(ep, mt, nt, row);

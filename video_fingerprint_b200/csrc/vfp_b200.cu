@@ -541,7 +541,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
   __nv_bfloat16* c3a = reinterpret_cast<__nv_bfloat16*>(conv_ws + L.c3);
   g_prof.launches += 4;
   {
-    const long long grid = std::min<long long>(F, (long long)device_sm_count() * 8);
+    const long long grid = std::min<long long>(F, (long long)device_sm_count() * 10);
     conv1_stem_kernel<<<(unsigned)grid, kC1Threads, 0, st>>>(frames, frame_dtype, F, w->c1_wpack, w->c1_bias, c1a);
     g_prof.mark(kStConv1, st);
   }
@@ -559,6 +559,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     EpiBiasActTma<true>::Params ep{};
     if (make_tmap_out(&ep.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (conv2 out)");
     ep.bias = w->c2_b; ep.N = 64; ep.act = 1;
+    // N = 64 is narrow: three row tiles per CTA tile, round-robin over three accumulators (see gemm_sm100.cuh)
     VFP_CUDA((launch_gemm<64, 64, 3, EpiBiasActTma<true>, 3>(ta, w->tm_c2, s, ep, st)));
     g_prof.mark(kStConv2, st);
   }
@@ -568,10 +569,11 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     s.m_tiles = (int)((F + 1) / 2); s.n_tiles = 1; s.k_blocks = 9; s.group_m = 16; s.a_conv = 1;
     s.tiles_per_frame = 1; s.frames_per_tile = 2; s.tile_out_rows = 8;
     conv_taps_strided(&s, 1);
-    EpiBiasActTma<true>::Params ep{};
+    EpiConvTransposedTma::Params ep{};
     if (make_tmap_out(&ep.tmap_out, c3a, (uint64_t)F * 64, 128, true)) return fail("tensor map encode failed (conv3 out)");
-    ep.bias = w->c3_b; ep.N = 128; ep.act = 1;
-    VFP_CUDA((launch_gemm<128, 64, 4, EpiBiasActTma<true>, 2>(ta, w->tm_c3, s, ep, st)));
+    ep.bias = w->c3_b; ep.c_out = 128; ep.pixels_per_tile = 256;
+    // channels on M (128), four frames (256 pixels) on N
+    VFP_CUDA((launch_gemm<128, 64, 4, EpiConvTransposedTma, 2, true>(ta, w->tm_c3, s, ep, st)));
     g_prof.mark(kStConv3, st);
   }
   {  // conv4: 8x8x128 -> 4x4x256 + ReLU + global average pool, tile = 8 frames
