@@ -204,6 +204,8 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     lib = _native.load()
+    if args.stem_pass:
+        lib.vfp_set_tuning(0, args.stem_pass)
     peaks = load_peaks()
 
     n_clips = args.clips
@@ -376,6 +378,7 @@ def main():
     ap.add_argument("--frames-per-pass", type=int, default=1 << 20)
     ap.add_argument("--join-n", type=int, default=262_144)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--stem-pass", type=int, default=0, help="experiment: frames per conv1+conv2 stem pass")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-join", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = (
     "vfp_profile_num_stages",
     "vfp_profile_stage_name",
     "vfp_profile_read",
+    "vfp_set_tuning",
 )
 
 
@@ -91,6 +92,8 @@ def load() -> C.CDLL:
     lib.vfp_profile_stage_name.argtypes = [i32]
     lib.vfp_profile_read.restype = i32
     lib.vfp_profile_read.argtypes = [vp, i32, vp, i32]
+    lib.vfp_set_tuning.restype = i32
+    lib.vfp_set_tuning.argtypes = [i32, C.c_longlong]
     lib.vfp_device_error_word.restype = C.c_uint
     lib.vfp_device_error_word.argtypes = []
     if lib.vfp_abi_version() != ABI_VERSION:

@@ -5,7 +5,20 @@
 
 namespace vfp {
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact (erf-form) GELU, nn.GELU() default (model.py:136). erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
+// far below the bf16 rounding of the stored activation): one exp, one reciprocal and a 5-term Horner chain instead of
+// erff's long polynomial - the MLP up-projection epilogue evaluates 2.6e9 of these per 10k clips on 8 warps per SM.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  const float erfc_z = p * t * __expf(-z * z);     // 1 - erf(|x|/sqrt2)
+  const float half_erfc = 0.5f * erfc_z;
+  return x >= 0.0f ? x * (1.0f - half_erfc) : x * half_erfc;
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);

@@ -120,9 +120,11 @@ __global__ void __launch_bounds__(256)
 temporal_conv_kernel(const float* __restrict__ x, const int* __restrict__ tok_pos, const int* __restrict__ tok_len,
                      const float* __restrict__ w /*[4][11][256]*/, const float* __restrict__ bias /*[256]*/,
                      float* __restrict__ y, int n_tokens) {
-  constexpr int TOK = 8;
+  // One CTA walks kTok consecutive packed tokens; thread = output channel. The 11-tap input window of the thread's
+  // 4 input channels slides through registers: one new float4 per token instead of 11.
+  constexpr int kTok = 32;
   const int o = threadIdx.x;
-  const int t0 = blockIdx.x * TOK;
+  const int t0 = blockIdx.x * kTok;
   float wr[4][11];
 #pragma unroll
   for (int ci = 0; ci < 4; ++ci)
@@ -130,20 +132,32 @@ temporal_conv_kernel(const float* __restrict__ x, const int* __restrict__ tok_po
     for (int tap = 0; tap < 11; ++tap) wr[ci][tap] = __ldg(w + (ci * 11 + tap) * kDim + o);
   const float b = __ldg(bias + o);
   const int cin = 4 * (o & 63);
-  for (int tt = 0; tt < TOK; ++tt) {
-    const int t = t0 + tt;
-    if (t >= n_tokens) break;
+  // win[i] = x[t + i - 5] (rows of neighbouring clips included; validity is decided per tap from (pos, len)).
+  // The row entering the window is fetched one iteration ahead so its latency overlaps the FMAs.
+  auto load_row = [&](int t) -> float4 {
+    return (t >= 0 && t < n_tokens) ? *reinterpret_cast<const float4*>(x + (size_t)t * kDim + cin) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 win[11];
+#pragma unroll
+  for (int i = 0; i < 11; ++i) win[i] = load_row(t0 + i - 5);
+  const int t_end = min(t0 + kTok, n_tokens);
+  for (int t = t0; t < t_end; ++t) {
+    const float4 incoming = load_row(t + 6);
+    const float self = x[(size_t)t * kDim + o];
     const int pos = tok_pos[t], len = tok_len[t];
     float acc = b;
 #pragma unroll
     for (int tap = 0; tap < 11; ++tap) {
       const int p = pos + tap - 5;
-      if (p >= 0 && p < len) {
-        const float4 xi = *reinterpret_cast<const float4*>(x + (size_t)(t + tap - 5) * kDim + cin);
+      if (p >= 0 && p < len) {  // zero padding at the clip ends (Conv1d padding=k//2 on a B=1 clip)
+        const float4 xi = win[tap];
         acc += wr[0][tap] * xi.x + wr[1][tap] * xi.y + wr[2][tap] * xi.z + wr[3][tap] * xi.w;
       }
     }
-    y[(size_t)t * kDim + o] = x[(size_t)t * kDim + o] + fmaxf(acc, 0.0f);
+    y[(size_t)t * kDim + o] = self + fmaxf(acc, 0.0f);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) win[i] = win[i + 1];
+    win[10] = incoming;
   }
 }
 

@@ -230,6 +230,9 @@ int prep_f32(vfp_weights* w, const float* src, size_t n, float** dev) {
 //     frame encoder walks the token pass in such slices and only leaves the 512 B/frame pooled features behind.
 // ---------------------------------------------------------------------------------------------
 constexpr int64_t kConvPassFrames = 16384;
+// conv1+conv2 sub-pass. Measured on B200 (10k x 64-frame clips): 512 -> 71.3 ms/step, 1024 -> 62.9, 2048 -> 60.7,
+// 4096 -> 58.9, 16384 -> 55.8: short L2-sized sub-passes lose more to small launches than they save in HBM traffic.
+int64_t g_stem_pass_frames = kConvPassFrames;
 
 struct TokenWs {
   size_t cu, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, h, logits, xbf, pooled, pooled_bf, head_h, total;
@@ -301,6 +304,11 @@ int vfp_device_sm_count(void) {
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
   return sms;
+}
+
+int vfp_set_tuning(int key, long long value) {
+  if (key == 0 && value >= 64) { g_stem_pass_frames = value; return 0; }
+  return 1;
 }
 
 int vfp_profile_enable(int on) {
@@ -539,30 +547,38 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
   __nv_bfloat16* c1a = reinterpret_cast<__nv_bfloat16*>(conv_ws + L.c1);
   __nv_bfloat16* c2a = reinterpret_cast<__nv_bfloat16*>(conv_ws + L.c2);
   __nv_bfloat16* c3a = reinterpret_cast<__nv_bfloat16*>(conv_ws + L.c3);
-  g_prof.launches += 4;
-  {
-    const long long grid = std::min<long long>(F, (long long)device_sm_count() * 10);
-    conv1_stem_kernel<<<(unsigned)grid, kC1Threads, 0, st>>>(frames, frame_dtype, F, w->c1_wpack, w->c1_bias, c1a);
-    g_prof.mark(kStConv1, st);
-  }
+  const size_t frame_bytes = (size_t)12288 * (frame_dtype == VFP_FRAME_U8 ? 1 : frame_dtype == VFP_FRAME_BF16 ? 2 : 4);
+  // conv1 + conv2 can run in shorter "stem passes" (vfp_set_tuning key 0) so that conv1's output (64 KB per frame,
+  // the largest tensor of the forward) is still in L2 when conv2 reads it; by default one stem pass = the conv pass.
   CUtensorMap ta;
-  {  // conv2: c1 is stored space-to-depth [frame][16][16][4*32] -> dense 2x2/stride-1 taps; tile = 8 rows x 16 cols
-    if (make_tmap_nhwc_bf16(&ta, c1a, F, 16, 16, 128, 64, 16, 8, 1, 1)) return fail("tensor map encode failed (conv2)");
-    GemmShape s{};
-    s.m_tiles = (int)(2 * F); s.n_tiles = 1; s.k_blocks = 6; s.group_m = 16; s.a_conv = 1;
-    s.tiles_per_frame = 2; s.frames_per_tile = 1; s.tile_out_rows = 8; s.h_mul = 1;
-    for (int kb = 0; kb < 6; ++kb) {
-      s.tap_c_blk[kb] = (signed char)kConv2KBlocks[kb].c_half;
-      s.tap_w[kb] = (signed char)kConv2KBlocks[kb].dw;
-      s.tap_h[kb] = (signed char)kConv2KBlocks[kb].dh;
+  for (int64_t s0 = 0; s0 < F; s0 += g_stem_pass_frames) {
+    const int64_t n = std::min<int64_t>(g_stem_pass_frames, F - s0);
+    g_prof.launches += 2;
+    {
+      const long long grid = std::min<long long>(n, (long long)device_sm_count() * 10);
+      conv1_stem_kernel<<<(unsigned)grid, kC1Threads, 0, st>>>(frames + (size_t)s0 * frame_bytes, frame_dtype, n, w->c1_wpack,
+                                                              w->c1_bias, c1a);
+      g_prof.mark(kStConv1, st);
     }
-    EpiBiasActTma<true>::Params ep{};
-    if (make_tmap_out(&ep.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (conv2 out)");
-    ep.bias = w->c2_b; ep.N = 64; ep.act = 1;
-    // N = 64 is narrow: three row tiles per CTA tile, round-robin over three accumulators (see gemm_sm100.cuh)
-    VFP_CUDA((launch_gemm<64, 64, 3, EpiBiasActTma<true>, 3>(ta, w->tm_c2, s, ep, st)));
-    g_prof.mark(kStConv2, st);
+    {  // conv2: c1 is stored space-to-depth [frame][16][16][4*32] -> dense 2x2/stride-1 taps; tile = 8 rows x 16 cols
+      if (make_tmap_nhwc_bf16(&ta, c1a, n, 16, 16, 128, 64, 16, 8, 1, 1)) return fail("tensor map encode failed (conv2)");
+      GemmShape s{};
+      s.m_tiles = (int)(2 * n); s.n_tiles = 1; s.k_blocks = 6; s.group_m = 16; s.a_conv = 1;
+      s.tiles_per_frame = 2; s.frames_per_tile = 1; s.tile_out_rows = 8; s.h_mul = 1; s.n_segments = 1;
+      for (int kb = 0; kb < 6; ++kb) {
+        s.tap_c_blk[kb] = (signed char)kConv2KBlocks[kb].c_half;
+        s.tap_w[kb] = (signed char)kConv2KBlocks[kb].dw;
+        s.tap_h[kb] = (signed char)kConv2KBlocks[kb].dh;
+      }
+      EpiBiasActTma<true>::Params ep{};
+      if (make_tmap_out(&ep.tmap_out, c2a + (size_t)s0 * 256 * 64, (uint64_t)n * 256, 64, true)) return fail("tensor map encode failed (conv2 out)");
+      ep.bias = w->c2_b; ep.N = 64; ep.act = 1;
+      // N = 64 is narrow: three row tiles per CTA tile, round-robin over three accumulators (see gemm_sm100.cuh)
+      VFP_CUDA((launch_gemm<64, 64, 3, EpiBiasActTma<true>, 3>(ta, w->tm_c2, s, ep, st)));
+      g_prof.mark(kStConv2, st);
+    }
   }
+  g_prof.launches += 2;
   {  // conv3: 16x16x64 -> 8x8x128 through a stride-2 box, tile = 2 frames
     if (make_tmap_nhwc_bf16(&ta, c2a, F, 16, 16, 64, 64, 8, 8, 2, 2)) return fail("tensor map encode failed (conv3)");
     GemmShape s{};
@@ -670,7 +686,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   }
   // ---- multi-scale temporal convolutions (residual) ----
   {
-    const unsigned grid = (unsigned)((F + 7) / 8);
+    const unsigned grid = (unsigned)((F + 31) / 32);
     temporal_conv_kernel<<<grid, 256, 0, st>>>(xa, tok_pos, tok_len, w->tc_w[0], w->tc_b[0], xb, (int)F);
     temporal_conv_kernel<<<grid, 256, 0, st>>>(xb, tok_pos, tok_len, w->tc_w[1], w->tc_b[1], xa, (int)F);
     g_prof.mark(kStTemporalConv, st);
