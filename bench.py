@@ -55,6 +55,16 @@ STAGE_FLOPS = {
 }
 
 
+# algorithmic HBM bytes per clip of the stages whose binding roofline is memory, not the tensor pipe
+STAGE_BYTES = {
+    "conv1_stem": (24576 + 65536) * _T,           # bf16 frame in, bf16 32x32x32 out
+    "conv2_igemm": (65536 + 32768) * _T,          # conv1 output in, 16x16x64 out
+    "conv3_igemm": (32768 + 16384) * _T,
+    "temporal_conv": 2 * (1024 + 1024) * _T,      # two blocks, fp32 stream in + out
+    "layernorm": 8 * (1024 + 512 + 1024 + 512) * _T,
+}
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -65,7 +75,8 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms; only the samples that fall INSIDE the timed region
+    (host timestamps taken around it) are reported. Started before the warm-up so nvidia-smi's start-up is not lost."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -75,7 +86,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             threading.Thread(target=self._pump, daemon=True).start()
@@ -84,21 +95,25 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin: float, t_end: float):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if t_begin <= t <= t_end + 0.05 and len(r) >= 6]
+        rows = inside if inside else [r for _, r in self.rows[-3:] if len(r) >= 6]
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({names[i] for r in rows for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
 
 def dist_setup(n_gpus: int):
@@ -224,24 +239,26 @@ def run_ours(args):
     def step():
         return model.fingerprint_packed(frames, lengths)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(3, args.warmup)):
         emb = step()
     barrier(world)
     stage_ms = (C.c_double * 32)()
     launches = C.c_uint64(0)
     lib.vfp_profile_read(stage_ms, 32, C.byref(launches), 1)  # reset the launch counter
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world)
+    t_begin = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
         emb = step()
     ev1.record()
     barrier(world)
+    t_end = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     lib.vfp_profile_read(stage_ms, 32, C.byref(launches), 1)
     gpu_launches = int(launches.value)
     # per-kernel times: one more step with the library's stage profiler on (CUDA events between the stages,
@@ -337,17 +354,30 @@ def run_ours(args):
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----
-    dom = max((k for k in stages if k in STAGE_FLOPS), key=lambda k: stages[k])
+    dom = max((k for k in stages if k in STAGE_FLOPS or k in STAGE_BYTES), key=lambda k: stages[k])
     token_passes = -(-n_clips * T_FRAMES // args.frames_per_pass)
     conv_passes = -(-min(n_clips * T_FRAMES, args.frames_per_pass) // 16384) * token_passes
     launches_per_step = conv_passes if dom.startswith("conv") else token_passes * (4 if dom.endswith("gemm") or dom in ("attention", "mlp1_gemm_gelu") else 1)
     dom_ms = stages[dom]
-    achieved = STAGE_FLOPS[dom] * n_clips / (dom_ms / 1000.0) / 1e12
+    tflops = STAGE_FLOPS.get(dom, 0) * n_clips / (dom_ms / 1000.0) / 1e12
+    gbs = STAGE_BYTES.get(dom, 0) * n_clips / (dom_ms / 1000.0) / 1e9
+    frac_t, frac_h = tflops / peaks["tc_sustained"], gbs / peaks["hbm"]
+    hbm_bound = frac_h > frac_t  # the binding roofline is the one the kernel sits closer to
     roofline = {
-        "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tc_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["tc_sustained"],
-        "traffic": None, "peak_source": f"{peaks['source']} (sustained bf16, kernel timed inside a long step)",
+        "bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
+        "achieved": gbs if hbm_bound else tflops, "peak": peaks["hbm"] if hbm_bound else peaks["tc_sustained"],
+        "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": frac_h if hbm_bound else frac_t, "traffic": None,
+        "peak_source": f"{peaks['source']} ({'HBM copy bandwidth' if hbm_bound else 'sustained bf16, kernel timed inside a long step'})",
+        "other_roofline": {"tensor_tflops": tflops, "tensor_frac": frac_t, "hbm_gbs": gbs, "hbm_frac": frac_h},
         "launches_per_step": launches_per_step, "ms_per_step_in_kernel": dom_ms,
+        "algorithmic_per_clip": {"flops": STAGE_FLOPS.get(dom), "bytes": STAGE_BYTES.get(dom)},
         "whole_step": {"achieved": value / world * FLOPS_PER_CLIP / 1e12, "frac": value / world * FLOPS_PER_CLIP / 1e12 / peaks["tc_sustained"], "unit": "TFLOP/s"},
+        "per_stage": {
+            k: {"ms": round(stages[k], 3),
+                "tflops": round(STAGE_FLOPS[k] * n_clips / (stages[k] / 1000.0) / 1e12, 1) if k in STAGE_FLOPS and stages[k] > 0 else None,
+                "gbs": round(STAGE_BYTES[k] * n_clips / (stages[k] / 1000.0) / 1e9, 1) if k in STAGE_BYTES and stages[k] > 0 else None}
+            for k in stages
+        },
     }
     line = {
         "metric": METRIC, "value": value, "unit": "videos/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),

@@ -37,6 +37,9 @@ extern "C" {
 #define VFP_FRAME_U8 0
 #define VFP_FRAME_BF16 1
 #define VFP_FRAME_F32 2
+/* decoder layout: (T, 64, 64, 3) uint8, the frames _preprocess_frames holds BEFORE its /255 + permute
+ * (fingerprint.py:210-212) - the on-device preprocess of SURVEY.md section 8(f) rank 2 */
+#define VFP_FRAME_U8_HWC 3
 
 typedef struct vfp_weights vfp_weights;
 

@@ -70,6 +70,10 @@ def test_input_dtypes_and_batched_forward():
     e_u8 = m(torch.round(x * 255).to(torch.uint8).cuda()).cpu()
     e_bf16 = m(x.to(torch.bfloat16).cuda()).cpu()
     e_cpu_in = m(x).cpu()                                 # host tensor is copied to the GPU, not computed on the CPU
+    # decoder layout (T, H, W, 3) uint8: the /255 + HWC->CHW of _preprocess_frames (fingerprint.py:210-212) fused in
+    hwc = torch.round(x * 255).to(torch.uint8).permute(0, 1, 3, 4, 2).reshape(-1, 64, 64, 3).contiguous()
+    e_hwc = m.fingerprint_packed(hwc.cuda(), [24] * 6).cpu()
+    assert torch.equal(e_hwc, e_u8)
     for e in (e_f32, e_u8, e_bf16, e_cpu_in):
         assert cosine(e, want).min() >= COS_BAR
     assert torch.equal(e_f32, e_cpu_in)

@@ -19,7 +19,7 @@ constexpr int kC1SmemElems = kC1PadH * kC1PadW * 3 + 8;
 constexpr int kC1CellPitch = 272;                 // 256 B cell + 16 B pad: conflict-free fragment stores
 constexpr int kC1StageBytes = 8 * kC1CellPitch;   // per warp: 8 cells
 
-enum FrameDtype : int { kFrameU8 = 0, kFrameBF16 = 1, kFrameF32 = 2 };
+enum FrameDtype : int { kFrameU8 = 0, kFrameBF16 = 1, kFrameF32 = 2, kFrameU8HWC = 3 };
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
@@ -69,10 +69,21 @@ conv1_stem_kernel(const void* __restrict__ frames, int frame_dtype, long long n_
         const int e = i * 4;
         const int c = e >> 12, h = (e >> 6) & 63, w = e & 63;
         __nv_bfloat16* d = tile + ((h + 2) * kC1PadW + (w + 2)) * 3 + c;
-        d[0] = __float2bfloat16((float)(q & 0xFF) * (1.0f / 255.0f));
-        d[3] = __float2bfloat16((float)((q >> 8) & 0xFF) * (1.0f / 255.0f));
-        d[6] = __float2bfloat16((float)((q >> 16) & 0xFF) * (1.0f / 255.0f));
-        d[9] = __float2bfloat16((float)(q >> 24) * (1.0f / 255.0f));
+        d[0] = __float2bfloat16((float)(q & 0xFF) / 255.0f);
+        d[3] = __float2bfloat16((float)((q >> 8) & 0xFF) / 255.0f);
+        d[6] = __float2bfloat16((float)((q >> 16) & 0xFF) / 255.0f);
+        d[9] = __float2bfloat16((float)(q >> 24) / 255.0f);
+      }
+    } else if (frame_dtype == kFrameU8HWC) {
+      // decoder layout (H, W, 3) uint8, i.e. what _preprocess_frames sees before its permute (fingerprint.py:210-212):
+      // a frame row is 192 contiguous bytes = 192 contiguous elements of the padded HWC tile
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(frames) + f * 12288);
+      for (int i = tid; i < 3072; i += kC1Threads) {
+        const uint32_t q = __ldg(src + i);
+        const int h = i / 48, k = (i - h * 48) * 4;
+        __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(tile + ((h + 2) * kC1PadW + 2) * 3 + k);
+        d[0] = __floats2bfloat162_rn((float)(q & 0xFF) / 255.0f, (float)((q >> 8) & 0xFF) / 255.0f);
+        d[1] = __floats2bfloat162_rn((float)((q >> 16) & 0xFF) / 255.0f, (float)(q >> 24) / 255.0f);
       }
     } else if (frame_dtype == kFrameBF16) {
       const uint2* src = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(frames) + f * 12288);

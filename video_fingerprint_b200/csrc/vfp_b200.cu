@@ -547,7 +547,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
   __nv_bfloat16* c1a = reinterpret_cast<__nv_bfloat16*>(conv_ws + L.c1);
   __nv_bfloat16* c2a = reinterpret_cast<__nv_bfloat16*>(conv_ws + L.c2);
   __nv_bfloat16* c3a = reinterpret_cast<__nv_bfloat16*>(conv_ws + L.c3);
-  const size_t frame_bytes = (size_t)12288 * (frame_dtype == VFP_FRAME_U8 ? 1 : frame_dtype == VFP_FRAME_BF16 ? 2 : 4);
+  const size_t frame_bytes = (size_t)12288 * (frame_dtype == VFP_FRAME_BF16 ? 2 : frame_dtype == VFP_FRAME_F32 ? 4 : 1);
   // conv1 + conv2 can run in shorter "stem passes" (vfp_set_tuning key 0) so that conv1's output (64 KB per frame,
   // the largest tensor of the forward) is still in L2 when conv2 reads it; by default one stem pass = the conv pass.
   CUtensorMap ta;
@@ -755,8 +755,8 @@ int vfp_forward(const vfp_weights* w, const void* frames, int frame_dtype, const
                 float* emb_out, float* features_out, void* workspace, size_t workspace_bytes, void* stream) {
   if (!w || !frames || !cu || !emb_out || !workspace) return fail("vfp_forward: null argument");
   if (n_clips <= 0) return fail("vfp_forward: n_clips must be positive");
-  if (frame_dtype < 0 || frame_dtype > 2) return fail("vfp_forward: unknown frame dtype");
-  const size_t frame_bytes = (size_t)12288 * (frame_dtype == VFP_FRAME_U8 ? 1 : frame_dtype == VFP_FRAME_BF16 ? 2 : 4);
+  if (frame_dtype < 0 || frame_dtype > 3) return fail("vfp_forward: unknown frame dtype");
+  const size_t frame_bytes = (size_t)12288 * (frame_dtype == VFP_FRAME_BF16 ? 2 : frame_dtype == VFP_FRAME_F32 ? 4 : 1);
   if (cu[0] != 0) return fail("vfp_forward: cu_seqlens[0] must be 0");
   int max_T = 0;
   for (int i = 0; i < n_clips; ++i) {
@@ -837,7 +837,7 @@ int vfp_join_threshold(const float* q, const float* db, int64_t n_q, int64_t n_d
   ep.thr = thr - screen_margin;
   ep.q_rows = n_q; ep.db_rows = n_db; ep.q_row0 = q_row0;
   ep.out_i = cand_i; ep.out_j = cand_j; ep.out_s = cand_s; ep.count = cand_count; ep.capacity = cand_cap;
-  VFP_CUDA((launch_gemm_bres<256, 64, 4, 4, EpiJoinThreshold>(ta, tb, s, ep, st)));
+  VFP_CUDA((launch_gemm<256, 64, 4, EpiJoinThreshold>(ta, tb, s, ep, st)));  // measured faster than the B-resident variant here
   rescore_pairs_kernel<<<device_sm_count() * 4, 256, 0, st>>>(q, db, dim, q_row0, cand_i, cand_j, cand_count, cand_cap, thr,
                                                               out_i, out_j, out_s, counts, capacity);
   // counts[1] = candidate count (device-side copy so the caller reads both with one transfer)

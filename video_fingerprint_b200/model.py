@@ -152,18 +152,22 @@ class VideoFingerprintAttention(nn.Module):
     # ------------------------------------------------------------------ packed (variable-length) entry
     @torch.no_grad()
     def fingerprint_packed(self, frames: torch.Tensor, lengths: Sequence[int], return_features: bool = False):
-        """frames: (sum T, 3, 64, 64) uint8 / bf16 / fp32 on the GPU, clips back to back; lengths: frames per clip.
+        """frames: (sum T, 3, 64, 64) uint8 / bf16 / fp32, or decoder-layout (sum T, 64, 64, 3) uint8, clips back to back;
+        lengths: frames per clip.
         Every clip gets exactly the embedding a B=1 reference forward on that clip alone would give."""
         _native.require_cuda()
         if self.training:
             raise RuntimeError("inference only: call .eval() first (the reference scanner does, fingerprint.py:33)")
         lengths = [int(t) for t in lengths]
         total = sum(lengths)
-        if frames.dim() != 4 or tuple(frames.shape[1:]) != (3, 64, 64) or frames.shape[0] != total:
-            raise ValueError(f"frames must be (sum(lengths)={total}, 3, 64, 64), got {tuple(frames.shape)}")
+        hwc = frames.dim() == 4 and tuple(frames.shape[1:]) == (64, 64, 3) and frames.dtype == torch.uint8
+        if frames.dim() != 4 or not (hwc or tuple(frames.shape[1:]) == (3, 64, 64)) or frames.shape[0] != total:
+            raise ValueError(f"frames must be (sum(lengths)={total}, 3, 64, 64) or uint8 (.., 64, 64, 3), got {tuple(frames.shape)}")
         if not frames.is_cuda:
             frames = frames.cuda()
-        if frames.dtype == torch.uint8:
+        if hwc:
+            code = _native.FRAME_U8_HWC  # decoder layout: /255 and HWC->CHW (fingerprint.py:210-212) happen in conv1's loader
+        elif frames.dtype == torch.uint8:
             code = _native.FRAME_U8
         elif frames.dtype == torch.bfloat16:
             code = _native.FRAME_BF16
