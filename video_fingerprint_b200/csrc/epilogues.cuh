@@ -125,9 +125,12 @@ struct EpiBiasActTma : EpiDefaults {
     int N;
     int act;                           // 0 none, 1 relu, 2 gelu(erf)
   };
+  // 16 epilogue warps on 256-column tiles (4 per TMEM lane quarter): the per-chunk chain tcgen05.ld -> math ->
+  // staging -> fence -> TMA issue is latency-bound, more warps overlap more of it. One staging buffer per warp.
+  static constexpr int kColumnSplit = 4;
   static constexpr int kChunkBytes = BF16_OUT ? 2048 : 4096;
-  static constexpr int kBuffers = 2;
-  static constexpr int kExtraSmemBytes = 8 * kBuffers * kChunkBytes;
+  static constexpr int kBuffers = 1;
+  static constexpr int kExtraSmemBytes = 16 * kBuffers * kChunkBytes;
   uint8_t* stage;
   int buf;
   __device__ __forceinline__ void setup(const Params&, uint8_t* extra, int warp_slot, int) {
@@ -189,7 +192,7 @@ struct EpiBiasActTma : EpiDefaults {
       tma_store_2d(&p.tmap_out, dst, col0, mt * 128 + (row & ~31));
       tma_store_commit();
     }
-    buf ^= 1;
+    buf = (buf + 1) % kBuffers;
   }
 };
 

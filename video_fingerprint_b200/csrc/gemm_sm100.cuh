@@ -18,10 +18,12 @@ namespace vfp {
 
 constexpr int kBlockM = 128;
 
-// Epilogues that only do column-local work let two warps share one TMEM lane quarter (each takes half of the
-// BLOCK_N columns); row-reducing epilogues keep one thread per row.
+// Epilogues that only do column-local work let two or four warps share one TMEM lane quarter (each takes a slice of
+// the BLOCK_N columns); row-reducing epilogues keep one thread per row.
 template <int BLOCK_N, class Epilogue>
-constexpr int gemm_column_split() { return (Epilogue::kColumnSplit == 2 && BLOCK_N >= 64) ? 2 : 1; }
+constexpr int gemm_column_split() {
+  return (Epilogue::kColumnSplit >= 4 && BLOCK_N >= 128) ? 4 : (Epilogue::kColumnSplit >= 2 && BLOCK_N >= 64) ? 2 : 1;
+}
 template <int BLOCK_N, class Epilogue>
 constexpr int gemm_threads() { return 64 + 128 * gemm_column_split<BLOCK_N, Epilogue>(); }
 
