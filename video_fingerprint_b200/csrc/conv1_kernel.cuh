@@ -28,6 +28,62 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// Copy frame f into the padded HWC bf16 tile (interior cells only; the halo stays zero). Any of the accepted frame
+// formats: planar CHW uint8 / bf16 / fp32 (what _preprocess_frames returns, fingerprint.py:210-214) or decoder-layout
+// HWC uint8. uint8 values are divided by 255 like the reference does.
+__device__ __forceinline__ void stage_frame_hwc(const void* __restrict__ frames, int frame_dtype, long long f,
+                                                __nv_bfloat16* __restrict__ tile, int tid, int nthreads) {
+  if (frame_dtype == kFrameU8) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(frames) + f * 12288);
+#pragma unroll 4
+    for (int i = tid; i < 3072; i += nthreads) {
+      const uint32_t q = __ldg(src + i);
+      const int e = i * 4;
+      const int c = e >> 12, h = (e >> 6) & 63, w = e & 63;
+      __nv_bfloat16* d = tile + ((h + 2) * kC1PadW + (w + 2)) * 3 + c;
+      d[0] = __float2bfloat16((float)(q & 0xFF) / 255.0f);
+      d[3] = __float2bfloat16((float)((q >> 8) & 0xFF) / 255.0f);
+      d[6] = __float2bfloat16((float)((q >> 16) & 0xFF) / 255.0f);
+      d[9] = __float2bfloat16((float)(q >> 24) / 255.0f);
+    }
+  } else if (frame_dtype == kFrameU8HWC) {
+    // decoder layout (H, W, 3) uint8, i.e. what _preprocess_frames sees before its permute (fingerprint.py:210-212):
+    // a frame row is 192 contiguous bytes = 192 contiguous elements of the padded HWC tile
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(frames) + f * 12288);
+#pragma unroll 4
+    for (int i = tid; i < 3072; i += nthreads) {
+      const uint32_t q = __ldg(src + i);
+      const int h = i / 48, k = (i - h * 48) * 4;
+      __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(tile + ((h + 2) * kC1PadW + 2) * 3 + k);
+      d[0] = __floats2bfloat162_rn((float)(q & 0xFF) / 255.0f, (float)((q >> 8) & 0xFF) / 255.0f);
+      d[1] = __floats2bfloat162_rn((float)((q >> 16) & 0xFF) / 255.0f, (float)(q >> 24) / 255.0f);
+    }
+  } else if (frame_dtype == kFrameBF16) {
+    const uint2* src = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(frames) + f * 12288);
+#pragma unroll 4
+    for (int i = tid; i < 3072; i += nthreads) {
+      const uint2 q = __ldg(src + i);
+      const int e = i * 4;
+      const int c = e >> 12, h = (e >> 6) & 63, w = e & 63;
+      __nv_bfloat16* d = tile + ((h + 2) * kC1PadW + (w + 2)) * 3 + c;
+      const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
+      const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
+      d[0] = lo.x; d[3] = lo.y; d[6] = hi.x; d[9] = hi.y;
+    }
+  } else {
+    const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(frames) + f * 12288);
+#pragma unroll 4
+    for (int i = tid; i < 3072; i += nthreads) {
+      const float4 q = __ldg(src + i);
+      const int e = i * 4;
+      const int c = e >> 12, h = (e >> 6) & 63, w = e & 63;
+      __nv_bfloat16* d = tile + ((h + 2) * kC1PadW + (w + 2)) * 3 + c;
+      d[0] = __float2bfloat16(q.x); d[3] = __float2bfloat16(q.y);
+      d[6] = __float2bfloat16(q.z); d[9] = __float2bfloat16(q.w);
+    }
+  }
+}
+
 // wpack: [5 kh][4 n-tiles][32 lanes][2] packed bf16x2 B fragments, bias: [32] fp32 (BN folded)
 __global__ void __launch_bounds__(kC1Threads)
 conv1_stem_kernel(const void* __restrict__ frames, int frame_dtype, long long n_frames,
@@ -61,52 +117,7 @@ conv1_stem_kernel(const void* __restrict__ frames, int frame_dtype, long long n_
   __syncthreads();
 
   for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
-    // ---- stage the frame: planar CHW -> padded HWC bf16 ----
-    if (frame_dtype == kFrameU8) {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(frames) + f * 12288);
-      for (int i = tid; i < 3072; i += kC1Threads) {
-        const uint32_t q = __ldg(src + i);
-        const int e = i * 4;
-        const int c = e >> 12, h = (e >> 6) & 63, w = e & 63;
-        __nv_bfloat16* d = tile + ((h + 2) * kC1PadW + (w + 2)) * 3 + c;
-        d[0] = __float2bfloat16((float)(q & 0xFF) / 255.0f);
-        d[3] = __float2bfloat16((float)((q >> 8) & 0xFF) / 255.0f);
-        d[6] = __float2bfloat16((float)((q >> 16) & 0xFF) / 255.0f);
-        d[9] = __float2bfloat16((float)(q >> 24) / 255.0f);
-      }
-    } else if (frame_dtype == kFrameU8HWC) {
-      // decoder layout (H, W, 3) uint8, i.e. what _preprocess_frames sees before its permute (fingerprint.py:210-212):
-      // a frame row is 192 contiguous bytes = 192 contiguous elements of the padded HWC tile
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(frames) + f * 12288);
-      for (int i = tid; i < 3072; i += kC1Threads) {
-        const uint32_t q = __ldg(src + i);
-        const int h = i / 48, k = (i - h * 48) * 4;
-        __nv_bfloat162* d = reinterpret_cast<__nv_bfloat162*>(tile + ((h + 2) * kC1PadW + 2) * 3 + k);
-        d[0] = __floats2bfloat162_rn((float)(q & 0xFF) / 255.0f, (float)((q >> 8) & 0xFF) / 255.0f);
-        d[1] = __floats2bfloat162_rn((float)((q >> 16) & 0xFF) / 255.0f, (float)(q >> 24) / 255.0f);
-      }
-    } else if (frame_dtype == kFrameBF16) {
-      const uint2* src = reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(frames) + f * 12288);
-      for (int i = tid; i < 3072; i += kC1Threads) {
-        const uint2 q = __ldg(src + i);
-        const int e = i * 4;
-        const int c = e >> 12, h = (e >> 6) & 63, w = e & 63;
-        __nv_bfloat16* d = tile + ((h + 2) * kC1PadW + (w + 2)) * 3 + c;
-        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&q.x);
-        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&q.y);
-        d[0] = lo.x; d[3] = lo.y; d[6] = hi.x; d[9] = hi.y;
-      }
-    } else {
-      const float4* src = reinterpret_cast<const float4*>(static_cast<const float*>(frames) + f * 12288);
-      for (int i = tid; i < 3072; i += kC1Threads) {
-        const float4 q = __ldg(src + i);
-        const int e = i * 4;
-        const int c = e >> 12, h = (e >> 6) & 63, w = e & 63;
-        __nv_bfloat16* d = tile + ((h + 2) * kC1PadW + (w + 2)) * 3 + c;
-        d[0] = __float2bfloat16(q.x); d[3] = __float2bfloat16(q.y);
-        d[6] = __float2bfloat16(q.z); d[9] = __float2bfloat16(q.w);
-      }
-    }
+    stage_frame_hwc(frames, frame_dtype, f, tile, tid, kC1Threads);
     __syncthreads();
 
     // ---- 64 m-tiles of 16 pixels, processed as 32 vertical PAIRS (output rows 2j, 2j+1; same 16 columns): in the

@@ -12,6 +12,7 @@
 #include "conv1_kernel.cuh"
 #include "gemm_launch.cuh"
 #include "join_kernels.cuh"
+#include "stem_fused_kernel.cuh"
 #include "token_kernels.cuh"
 #include "topk_kernels.cuh"
 
@@ -112,6 +113,8 @@ struct vfp_weights {
   __nv_bfloat16 *c2_w = nullptr, *c3_w = nullptr, *c4_w = nullptr;
   float *c2_b = nullptr, *c3_b = nullptr, *c4_b = nullptr;
   CUtensorMap tm_c2, tm_c3, tm_c4;
+  __nv_bfloat16* c2f_w = nullptr;  // conv2 weights in the K order of the fused stem kernel
+  CUtensorMap tm_c2f;
   // token embedding (Linear 256->S o Linear S->256, folded) + positional table
   __nv_bfloat16* wtok = nullptr;
   float* btok = nullptr;
@@ -233,6 +236,7 @@ constexpr int64_t kConvPassFrames = 16384;
 // conv1+conv2 sub-pass. Measured on B200 (10k x 64-frame clips): 512 -> 71.3 ms/step, 1024 -> 62.9, 2048 -> 60.7,
 // 4096 -> 58.9, 16384 -> 55.8: short L2-sized sub-passes lose more to small launches than they save in HBM traffic.
 int64_t g_stem_pass_frames = kConvPassFrames;
+int g_fused_stem = 1;  // conv1+conv2 in one kernel (conv1 output stays in shared memory); 0 = two kernels through HBM
 
 struct TokenWs {
   size_t cu, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, h, logits, xbf, pooled, pooled_bf, head_h, total;
@@ -308,6 +312,7 @@ int vfp_device_sm_count(void) {
 
 int vfp_set_tuning(int key, long long value) {
   if (key == 0 && value >= 64) { g_stem_pass_frames = value; return 0; }
+  if (key == 1) { g_fused_stem = value != 0; return 0; }
   return 1;
 }
 
@@ -407,6 +412,20 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
       bf[co] = cb[co] * bn.scale[co] + bn.shift[co];
     }
     if (upload(w, to_bf16(wf), &w->c2_w) || upload(w, bf, &w->c2_b)) return bail("");
+    // fused stem kernel (stem_fused_kernel.cuh): K block kb = (dh == 0 ? x : 3 + x), x = 0/1/2 <-> kw = 1/2/0,
+    // inside a block k = sh*32 + c with kh = 1 + sh for dh = 0, kh = 0 for (dh = -1, sh = 1), zero for (dh = -1, sh = 0)
+    std::vector<float> wfu((size_t)64 * 384, 0.0f);
+    const int kw_of_x[3] = {1, 2, 0};
+    for (int co = 0; co < 64; ++co)
+      for (int kb = 0; kb < 6; ++kb)
+        for (int sh = 0; sh < 2; ++sh) {
+          const int x = kb % 3, kw = kw_of_x[x];
+          const int kh = kb < 3 ? 1 + sh : (sh == 1 ? 0 : -1);
+          if (kh < 0) continue;
+          for (int c = 0; c < 32; ++c)
+            wfu[(size_t)co * 384 + kb * 64 + sh * 32 + c] = cw[((co * 32 + c) * 3 + kh) * 3 + kw] * bn.scale[co];
+        }
+    if (upload(w, to_bf16(wfu), &w->c2f_w)) return bail("");
   }
   if (prep_conv3x3(w, t, 6, 64, 128, &w->c3_w, &w->c3_b, &err)) return bail(err);
   if (prep_conv3x3(w, t, 9, 128, 256, &w->c4_w, &w->c4_b, &err)) return bail(err);
@@ -520,6 +539,7 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
     }
   }
   if (make_tmap_rows_bf16(&w->tm_c2, w->c2_w, 64, 384, 384, 64, 64) ||
+      make_tmap_rows_bf16(&w->tm_c2f, w->c2f_w, 64, 384, 384, 64, 64) ||
       make_tmap_rows_bf16(&w->tm_c3, w->c3_w, 128, 576, 576, 128, 64) ||
       make_tmap_rows_bf16(&w->tm_c4, w->c4_w, 256, 1152, 1152, 256, 64) ||
       make_tmap_rows_bf16(&w->tm_tok, w->wtok, kDim, 256, 256, 256, 64) ||
@@ -551,7 +571,23 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
   // conv1 + conv2 can run in shorter "stem passes" (vfp_set_tuning key 0) so that conv1's output (64 KB per frame,
   // the largest tensor of the forward) is still in L2 when conv2 reads it; by default one stem pass = the conv pass.
   CUtensorMap ta;
-  for (int64_t s0 = 0; s0 < F; s0 += g_stem_pass_frames) {
+  if (g_fused_stem) {
+    StemParams sp{};
+    sp.tmap_w = w->tm_c2f;
+    if (make_tmap_out(&sp.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (stem out)");
+    sp.frames = frames; sp.frame_dtype = frame_dtype; sp.n_frames = F;
+    sp.c1_wpack = w->c1_wpack; sp.c1_bias = w->c1_bias; sp.c2_bias = w->c2_b;
+    static bool configured = false;
+    if (!configured) {
+      VFP_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::kTotal));
+      configured = true;
+    }
+    g_prof.launches += 1;
+    const int grid = (int)std::min<int64_t>(F, device_sm_count());
+    stem_fused_kernel<<<grid, kStemThreads, StemSmem::kTotal, st>>>(sp);
+    g_prof.mark(kStConv2, st);  // the fused kernel is accounted under conv2; conv1 shows 0
+  }
+  for (int64_t s0 = 0; s0 < F && !g_fused_stem; s0 += g_stem_pass_frames) {
     const int64_t n = std::min<int64_t>(g_stem_pass_frames, F - s0);
     g_prof.launches += 2;
     {
