@@ -117,7 +117,8 @@ const char* vfp_profile_stage_name(int i);
 int vfp_profile_read(double* stage_ms, int n_stages, uint64_t* launches, int reset);
 
 /* Tuning knobs for experiments (process-wide). key 0: frames per conv1+conv2 stem pass of the
- * unfused path (default 16384 = the conv pass, >= 64); key 1: 1 = fused conv1+conv2 stem kernel (default), 0 = two kernels. */
+ * unfused path (default 16384 = the conv pass, >= 64); key 1: 1 = fused conv1+conv2 stem kernel (experimental,
+ * slower than the default two-kernel path in round 1), 0 = two kernels (default). */
 int vfp_set_tuning(int key, long long value);
 
 /* Reads and clears the device-side error word set by a kernel watchdog (0 = none). Synchronises. */

@@ -119,6 +119,22 @@ def test_return_features_and_layout_quirk():
     assert torch.allclose(emb2, emb, atol=1e-6)
 
 
+def test_fused_stem_matches():
+    """The experimental fused conv1+conv2 kernel (vfp_set_tuning(1, 1)) computes the same thing as the default path."""
+    lib = _native.load()
+    m = model_for(2, "stress")
+    clips = make_clips(41, [37, 64, 10, 150, 21], "colour")
+    ref = m.fingerprint_clips(clips).cpu()
+    try:
+        lib.vfp_set_tuning(1, 1)
+        fused = m.fingerprint_clips(clips).cpu()
+    finally:
+        lib.vfp_set_tuning(1, 0)
+    assert cosine(fused, ref).min() > 0.999995
+    assert (fused - ref).abs().max() < 2e-3
+    assert lib.vfp_device_error_word() == 0
+
+
 def test_non_default_architecture():
     m = vfp.create_model("attention", spatial_dim=64, embedding_dim=128, num_attention_blocks=2).eval()
     torch.manual_seed(5)

@@ -3,13 +3,15 @@
 // is 84 GB of the ~200 GB of HBM traffic of 10k clips), and both stand-alone kernels sit on the HBM roofline. Here it
 // never leaves the SM: the frame goes in (12-48 KB), conv2's output comes out (32 KB).
 //
-// One CTA per SM, persistent over frames, 18 warps:
-//   warp 0      conv2 weights -> smem by TMA (once), TMEM allocation
-//   warp 1      UMMA issuer (one lane)
-//   warps 2-5   conv2 epilogue: TMEM -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store
-//   warps 6-13  conv1 producers: mma.sync on the staged frame, results written straight into conv2's A-operand
-//               buffers in the canonical K-major SWIZZLE_128B layout
-//   warps 14-17 frame loaders: global -> padded HWC bf16 tile (double buffered)
+// One CTA per SM, persistent over frames, 30 warps (960 threads, 64 registers each - every role is written to fit):
+//   warp 0       conv2 weights -> smem by TMA (once), TMEM allocation
+//   warp 1       UMMA issuer (one lane)
+//   warps 2-5    conv2 epilogue: TMEM -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store
+//   warps 6-21   conv1 producers: mma.sync on the staged frame (B fragments re-read from shared memory to save
+//                registers), results written straight into conv2's A-operand buffers (K-major SWIZZLE_128B)
+//   warps 22-29  frame loaders: global -> padded HWC bf16 tile (double buffered)
+// The stand-alone conv1 kernel needs ~20 resident warps per SM to hide its latencies; 16 producer warps is what
+// fits next to the other roles.
 //
 // Work unit = half a frame = 128 conv2 output pixels (cell rows 8*hf .. 8*hf+7 of the 16x16 output). conv1's output is
 // kept space-to-depth (cell = 2x2 pixels, sub-pixel (sh, sw)), which turns conv2's stride-2 taps into row/column
@@ -26,9 +28,10 @@
 
 namespace vfp {
 
-constexpr int kStemThreads = 576;
-constexpr int kStemProducerWarp0 = 6, kStemProducerWarps = 8;
-constexpr int kStemLoaderWarp0 = 14, kStemLoaderWarps = 4;
+constexpr int kStemThreads = 960;
+constexpr int kStemProducerWarp0 = 6, kStemProducerWarps = 16;
+constexpr int kStemLoaderWarp0 = 22, kStemLoaderWarps = 8;
+constexpr int kStemC1WBytes = 5 * 4 * 32 * 8;      // conv1 B fragments: [kh][n-tile][lane] x 8 B
 constexpr int kStemABuf = 9 * 16 * 128;            // one of AL0 / AL1 / SH1: 18432 B
 constexpr int kStemUnitBytes = 3 * kStemABuf;      // 55296 B
 constexpr int kStemTileBytes = (kC1SmemElems * 2 + 127) / 128 * 128;
@@ -38,7 +41,8 @@ struct StemSmem {
   static constexpr int kW = kC1 + 2 * kStemUnitBytes;             // 6 weight tiles of 64 rows x 128 B
   static constexpr int kStage = kW + 6 * 8192;                    // 4 epilogue warps x 2 KB
   static constexpr int kTile = kStage + 4 * 2048;                 // 2 frame tiles
-  static constexpr int kBars = kTile + 2 * kStemTileBytes;
+  static constexpr int kC1W = kTile + 2 * kStemTileBytes;
+  static constexpr int kBars = kC1W + kStemC1WBytes;
   static constexpr int kTotal = kBars + 256 + 1024;
 };
 static_assert(StemSmem::kTotal <= 232448, "stem kernel shared memory");
@@ -79,6 +83,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
   // zero everything that is read before it is written: c1 halo rows / SH1 column 0, the tile halos
   for (int i = tid; i < (2 * kStemUnitBytes) / 16; i += kStemThreads) reinterpret_cast<uint4*>(c1buf)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < (2 * kStemTileBytes) / 16; i += kStemThreads) reinterpret_cast<uint4*>(smem + StemSmem::kTile)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < kStemC1WBytes / 8; i += kStemThreads)
+    reinterpret_cast<uint2*>(smem + StemSmem::kC1W)[i] = __ldg(reinterpret_cast<const uint2*>(p.c1_wpack) + i);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_w);
     tma_prefetch_desc(&p.tmap_out);
@@ -149,36 +155,39 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
       const int b = (int)(u & 1);
       const uint32_t ph = (uint32_t)((u >> 1) & 1);
       const long long frame = blockIdx.x + (u >> 1) * gridDim.x;
-      mbar_wait(&acc_full[b], ph);
+      mbar_wait_relaxed(&acc_full[b], ph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + b * 128;
 #pragma unroll 1
       for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint32_t v0[32], v1[32];
-        tmem_ld_32x32(taddr + c0, v0);
-        tmem_ld_32x32(taddr + 64 + c0, v1);
-        tmem_ld_wait();
-        float x[32];
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.c2_bias + c0 + i));
-          x[i] = fmaxf(__uint_as_float(v0[i]) + __uint_as_float(v1[i]) + bb.x, 0.0f);
-          x[i + 1] = fmaxf(__uint_as_float(v0[i + 1]) + __uint_as_float(v1[i + 1]) + bb.y, 0.0f);
-          x[i + 2] = fmaxf(__uint_as_float(v0[i + 2]) + __uint_as_float(v1[i + 2]) + bb.z, 0.0f);
-          x[i + 3] = fmaxf(__uint_as_float(v0[i + 3]) + __uint_as_float(v1[i + 3]) + bb.w, 0.0f);
-        }
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
         uint8_t* r0 = dst + lane * 64;
         const int sw = (lane >> 1) & 3;
+        if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the staging tile
+        __syncwarp();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint4 q;
-          q.x = pack_bf16x2(x[8 * c + 0], x[8 * c + 1]);
-          q.y = pack_bf16x2(x[8 * c + 2], x[8 * c + 3]);
-          q.z = pack_bf16x2(x[8 * c + 4], x[8 * c + 5]);
-          q.w = pack_bf16x2(x[8 * c + 6], x[8 * c + 7]);
-          *reinterpret_cast<uint4*>(r0 + ((c ^ sw) << 4)) = q;
+        for (int h = 0; h < 2; ++h) {  // 16 columns at a time keeps this role under 64 registers
+          uint32_t v0[16], v1[16];
+          tmem_ld_32x16(taddr + c0 + 16 * h, v0);
+          tmem_ld_32x16(taddr + 64 + c0 + 16 * h, v1);
+          tmem_ld_wait();
+          float x[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.c2_bias + c0 + 16 * h + i));
+            x[i] = fmaxf(__uint_as_float(v0[i]) + __uint_as_float(v1[i]) + bb.x, 0.0f);
+            x[i + 1] = fmaxf(__uint_as_float(v0[i + 1]) + __uint_as_float(v1[i + 1]) + bb.y, 0.0f);
+            x[i + 2] = fmaxf(__uint_as_float(v0[i + 2]) + __uint_as_float(v1[i + 2]) + bb.z, 0.0f);
+            x[i + 3] = fmaxf(__uint_as_float(v0[i + 3]) + __uint_as_float(v1[i + 3]) + bb.w, 0.0f);
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            uint4 q;
+            q.x = pack_bf16x2(x[8 * c + 0], x[8 * c + 1]);
+            q.y = pack_bf16x2(x[8 * c + 2], x[8 * c + 3]);
+            q.z = pack_bf16x2(x[8 * c + 4], x[8 * c + 5]);
+            q.w = pack_bf16x2(x[8 * c + 6], x[8 * c + 7]);
+            *reinterpret_cast<uint4*>(r0 + (((2 * h + c) ^ sw) << 4)) = q;
+          }
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -196,15 +205,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
     // ------------------------------ conv1 producers ------------------------------
     const int pw = warp - kStemProducerWarp0;
     const int g = lane >> 2, tig = lane & 3;
-    uint32_t bfrag[5][4][2];
-#pragma unroll
-    for (int kh = 0; kh < 5; ++kh)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.c1_wpack) + (kh * 4 + nt) * 32 + lane);
-        bfrag[kh][nt][0] = w.x;
-        bfrag[kh][nt][1] = w.y;
-      }
+    const uint2* wfrag = reinterpret_cast<const uint2*>(smem + StemSmem::kC1W) + lane;  // [(kh*4+nt)*32 + lane]
     float bia[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
@@ -214,11 +215,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
     for (long long li = 0; li < n_local; ++li) {
       const int t = (int)(li & 1);
       const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(smem + StemSmem::kTile + t * kStemTileBytes);
-      mbar_wait(&tile_full[t], (uint32_t)((li >> 1) & 1));
+      mbar_wait_relaxed(&tile_full[t], (uint32_t)((li >> 1) & 1));
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
         uint8_t* unit = c1buf + hf * kStemUnitBytes;
-        mbar_wait(&c1_empty[hf], (uint32_t)((li & 1) ^ 1));
+        mbar_wait_relaxed(&c1_empty[hf], (uint32_t)((li & 1) ^ 1));
         // conv1 output rows of this unit: hf = 0 -> 0..15 ; hf = 1 -> 14..31 (rows 14, 15 are the halo cell row,
         // recomputed instead of shared with the other buffer). m-tile = one row x 16 columns.
         const int row_first = hf == 0 ? 0 : 14;
@@ -242,7 +243,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
             a[2] = tile32[base_lo + tig + 4];
             a[3] = tile32[base_hi + tig + 4];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[nt], a, bfrag[kh][nt]);
+            for (int nt = 0; nt < 4; ++nt) {
+              const uint2 wv = wfrag[(kh * 4 + nt) * 32];
+              const uint32_t bq[2] = {wv.x, wv.y};
+              mma_bf16_16816(acc[nt], a, bq);
+            }
           }
           // scatter into the A-operand buffers. pixel (oh, ow): cell (oh/2, ow/2), sub (sh, sw) = (oh%2, ow%2);
           // buffer row = (cell_row - 8*hf + 1) * 16 + cell_col; 16-byte chunk j = sh*4 + nt, stored at j ^ (row % 8).
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
     const int ltid = tid - kStemLoaderWarp0 * 32;
     for (long long li = 0; li < n_local; ++li) {
       const int t = (int)(li & 1);
-      mbar_wait(&tile_empty[t], (uint32_t)(((li >> 1) & 1) ^ 1));
+      mbar_wait_relaxed(&tile_empty[t], (uint32_t)(((li >> 1) & 1) ^ 1));
       const long long frame = blockIdx.x + li * gridDim.x;
       stage_frame_hwc(p.frames, p.frame_dtype, frame, reinterpret_cast<__nv_bfloat16*>(smem + StemSmem::kTile + t * kStemTileBytes), ltid,
                       kStemLoaderWarps * 32);

@@ -236,7 +236,12 @@ constexpr int64_t kConvPassFrames = 16384;
 // conv1+conv2 sub-pass. Measured on B200 (10k x 64-frame clips): 512 -> 71.3 ms/step, 1024 -> 62.9, 2048 -> 60.7,
 // 4096 -> 58.9, 16384 -> 55.8: short L2-sized sub-passes lose more to small launches than they save in HBM traffic.
 int64_t g_stem_pass_frames = kConvPassFrames;
-int g_fused_stem = 1;  // conv1+conv2 in one kernel (conv1 output stays in shared memory); 0 = two kernels through HBM
+// conv1+conv2 in one kernel (stem_fused_kernel.cuh: conv1's output stays in shared memory as conv2's UMMA operand).
+// Correct (tests/test_forward_gpu.py::test_fused_stem_matches) but measured SLOWER than the two HBM-bound kernels
+// (33.1 ms vs 13.4 + 12.9 ms per 10k clips): its 16 mma.sync producer warps are instruction-issue bound (~300
+// instructions per 16-pixel m-tile incl. the swizzled scatter). Kept behind vfp_set_tuning(1, 1) as the starting
+// point for the next round; the default stays on the two-kernel path.
+int g_fused_stem = 0;
 
 struct TokenWs {
   size_t cu, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, h, logits, xbf, pooled, pooled_bf, head_h, total;
