@@ -130,8 +130,9 @@ def test_fused_stem_matches():
         fused = m.fingerprint_clips(clips).cpu()
     finally:
         lib.vfp_set_tuning(1, 0)
-    assert cosine(fused, ref).min() > 0.999995
-    assert (fused - ref).abs().max() < 2e-3
+    want = torch.stack(fingerprint_clips(make_state_dict(2, "stress"), clips))
+    assert cosine(fused, want).min() >= COS_BAR          # same bar as the default path
+    assert cosine(fused, ref).min() > 0.9999             # bf16 conv1 output, different summation order (split-K)
     assert lib.vfp_device_error_word() == 0
 
 
