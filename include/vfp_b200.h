@@ -118,11 +118,17 @@ int vfp_profile_read(double* stage_ms, int n_stages, uint64_t* launches, int res
 
 /* Tuning knobs for experiments (process-wide). key 0: frames per conv1+conv2 stem pass of the
  * unfused path (default 16384 = the conv pass, >= 64); key 1: 1 = fused conv1+conv2 stem kernel (experimental,
- * slower than the default two-kernel path in round 1), 0 = two kernels (default). */
+ * slower than the default two-kernel path in round 1), 0 = two kernels (default); key 2: 1 = hang diagnosis
+ * mode (see vfp_debug_hang_log), 0 = watchdog traps (default). */
 int vfp_set_tuning(int key, long long value);
 
 /* Reads and clears the device-side error word set by a kernel watchdog (0 = none). Synchronises. */
 unsigned int vfp_device_error_word(void);
+
+/* Hang diagnosis (development aid). After vfp_set_tuning(2, 1) a kernel whose mbarrier wait times out logs
+ * (barrier shared-memory address, parity, threadIdx.x, blockIdx.x) and abandons the wait instead of trapping;
+ * this returns up to max_entries such 4-word records (at most 64 are kept), or -1 on a CUDA error. Synchronises. */
+int vfp_debug_hang_log(unsigned int* out, int max_entries);
 
 #ifdef __cplusplus
 }

@@ -120,20 +120,29 @@ def test_return_features_and_layout_quirk():
 
 
 def test_fused_stem_matches():
-    """The experimental fused conv1+conv2 kernel (vfp_set_tuning(1, 1)) computes the same thing as the default path."""
+    """The fused conv1+conv2 stem kernel (vfp_set_tuning(1, 1)) against the two-kernel path and the oracle, for every
+    frame format it takes (planar bf16 / planar uint8 / decoder-layout uint8; fp32 frames stay on the two-kernel path).
+    More frames than SMs so every CTA walks several frames and the ring / double buffers wrap."""
     lib = _native.load()
+    sd = make_state_dict(2, "stress")
     m = model_for(2, "stress")
-    clips = make_clips(41, [37, 64, 10, 150, 21], "colour")
-    ref = m.fingerprint_clips(clips).cpu()
-    try:
-        lib.vfp_set_tuning(1, 1)
-        fused = m.fingerprint_clips(clips).cpu()
-    finally:
-        lib.vfp_set_tuning(1, 0)
-    want = torch.stack(fingerprint_clips(make_state_dict(2, "stress"), clips))
-    assert cosine(fused, want).min() >= COS_BAR          # same bar as the default path
-    assert cosine(fused, ref).min() > 0.9999             # bf16 conv1 output, different summation order (split-K)
-    assert lib.vfp_device_error_word() == 0
+    lengths = [37, 64, 10, 150, 21, 300, 47]
+    clips = make_clips(41, lengths, "colour")             # on the uint8/255 grid
+    want = torch.stack(fingerprint_clips(sd, clips))
+    x = torch.cat(clips)                                   # (sum T, 3, 64, 64) fp32
+    u8 = torch.round(x * 255).to(torch.uint8)
+    inputs = {"bf16": x.to(torch.bfloat16), "u8": u8, "u8_hwc": u8.permute(0, 2, 3, 1).contiguous()}
+    for name, frames in inputs.items():
+        frames = frames.cuda()
+        ref = m.fingerprint_packed(frames, lengths).cpu()
+        try:
+            lib.vfp_set_tuning(1, 1)
+            fused = m.fingerprint_packed(frames, lengths).cpu()
+        finally:
+            lib.vfp_set_tuning(1, 0)
+        assert lib.vfp_device_error_word() == 0, name
+        assert cosine(fused, want).min() >= COS_BAR, name     # same bar as the default path
+        assert cosine(fused, ref).min() > 0.99995, name        # same bf16 conv1 output, different summation order
 
 
 def test_non_default_architecture():

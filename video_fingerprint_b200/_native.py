@@ -34,6 +34,7 @@ EXPORTED_SYMBOLS = (
     "vfp_profile_stage_name",
     "vfp_profile_read",
     "vfp_set_tuning",
+    "vfp_debug_hang_log",
 )
 
 
@@ -94,6 +95,8 @@ def load() -> C.CDLL:
     lib.vfp_profile_read.argtypes = [vp, i32, vp, i32]
     lib.vfp_set_tuning.restype = i32
     lib.vfp_set_tuning.argtypes = [i32, C.c_longlong]
+    lib.vfp_debug_hang_log.restype = i32
+    lib.vfp_debug_hang_log.argtypes = [C.c_void_p, i32]
     lib.vfp_device_error_word.restype = C.c_uint
     lib.vfp_device_error_word.argtypes = []
     if lib.vfp_abi_version() != ABI_VERSION:

@@ -81,6 +81,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Hang diagnosis (vfp_set_tuning(2, 1)): instead of trapping, a timed-out wait records (barrier smem address, parity,
+// thread, block) in g_vfp_hang_log and RETURNS, so the kernel drains (with garbage results) and the host can read
+// which barrier never completed. Off by default.
+__device__ int g_vfp_hang_mode = 0;
+__device__ unsigned int g_vfp_hang_count = 0;
+__device__ unsigned int g_vfp_hang_log[64 * 4];
+
 // Wait used by whole warps (epilogue / producer / loader roles): polling in a tight loop costs issue slots that the
 // working warps of the same SM need (ncu on the fused stem kernel: ~60 % of all executed instructions were these
 // loops), so back off with nanosleep between polls. The single-lane TMA / UMMA roles keep the tight mbar_wait.
@@ -92,10 +99,23 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     __nanosleep(spins < 16 ? 32 : 128);
     if ((++spins & 0x3FFF) == 0) {
       if (t0 == 0) t0 = clock64();
-      else if (clock64() - t0 > 4000000000LL) {
-        atomicExch(&g_vfp_device_error, (unsigned int)kErrMbarTimeout);
-        __threadfence_system();
-        asm volatile("trap;");
+      else {
+        const int mode = *reinterpret_cast<volatile int*>(&g_vfp_hang_mode);
+        if (clock64() - t0 > (mode ? 400000000LL : 4000000000LL)) {
+          atomicExch(&g_vfp_device_error, (unsigned int)kErrMbarTimeout);
+          if (mode) {
+            const unsigned int i = atomicAdd(&g_vfp_hang_count, 1u);
+            if (i < 64) {
+              g_vfp_hang_log[4 * i] = smem_u32(bar);
+              g_vfp_hang_log[4 * i + 1] = parity;
+              g_vfp_hang_log[4 * i + 2] = threadIdx.x;
+              g_vfp_hang_log[4 * i + 3] = blockIdx.x;
+            }
+            return;
+          }
+          __threadfence_system();
+          asm volatile("trap;");
+        }
       }
     }
   }
@@ -198,6 +218,14 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
 }
 
 // ------------------------------------------------------------------------------------------

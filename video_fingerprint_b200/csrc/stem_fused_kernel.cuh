@@ -1,106 +1,148 @@
 // Fused frame-encoder stem: conv1 (3->32, k5 s2, mma.sync) feeding conv2 (32->64, k3 s2, tcgen05) through SHARED
 // MEMORY. conv1's output is the largest tensor of the whole forward (64 KB per frame: written once and read once it
-// is 84 GB of the ~200 GB of HBM traffic of 10k clips), and both stand-alone kernels sit on the HBM roofline. Here it
-// never leaves the SM: the frame goes in (12-48 KB), conv2's output comes out (32 KB).
+// is 84 GB of the ~200 GB of HBM traffic of 10k clips), and both stand-alone kernels sit on the HBM / L2->SM fill
+// roofline. Here it never leaves the SM: the frame goes in (12-24 KB), conv2's output comes out (32 KB).
 //
-// One CTA per SM, persistent over frames, 30 warps (960 threads, 64 registers each - every role is written to fit):
-//   warp 0       conv2 weights -> smem by TMA (once), TMEM allocation
-//   warp 1       UMMA issuer (one lane)
-//   warps 2-5    conv2 epilogue: TMEM -> +bias, ReLU -> bf16 -> swizzled staging -> TMA store
-//   warps 6-21   conv1 producers: mma.sync on the staged frame (B fragments re-read from shared memory to save
-//                registers), results written straight into conv2's A-operand buffers (K-major SWIZZLE_128B)
-//   warps 22-29  frame loaders: global -> padded HWC bf16 tile (double buffered)
-// The stand-alone conv1 kernel needs ~20 resident warps per SM to hide its latencies; 16 producer warps is what
-// fits next to the other roles.
+// One CTA per SM, persistent over frames, 24 warps = 6 warpgroups, registers re-balanced with setmaxnreg:
+//   WG0   warp 0        bulk-copy issuer: raw frame planes -> smem ring (cp.async.bulk, 5 slots = 1.7 frames of
+//                       prefetch), conv2 weights -> smem once (TMA)
+//         warp 1        TMEM allocation + UMMA issuer (one lane)
+//         warps 2-3     transposers: raw planar (or decoder-layout) frame -> zero-haloed HWC bf16 tile (double buffered)
+//   WG1-2 warps 4-11    conv2 epilogue: TMEM -> split-K sum, shifted-tap add, bias, ReLU -> bf16 -> staging -> TMA store
+//   WG3-5 warps 12-23   conv1 producers: mma.sync on the HWC tile, result written straight into conv2's A-operand
+//                       buffers (K-major SWIZZLE_128B) with conflict-free 16-byte stores
 //
 // Work unit = half a frame = 128 conv2 output pixels (cell rows 8*hf .. 8*hf+7 of the 16x16 output). conv1's output is
-// kept space-to-depth (cell = 2x2 pixels, sub-pixel (sh, sw)), which turns conv2's stride-2 taps into row/column
-// shifts of whole cells: tap kh -> (dh, sh) = (-1,1),(0,0),(0,1), same for kw. Three buffers per unit, each 9 cell rows
-// (1 halo + 8) x 16 cells x 128 B (64 channels = sub-rows sh=0,1 of one sw):
-//   AL0: sub-column sw=0          -> taps kw=1        AL1: sw=1 -> taps kw=2
-//   SH1: AL1 shifted right by one cell (column 0 = zero padding) -> taps kw=0 (input column 2*ow-1)
+// kept space-to-depth (cell = 2x2 pixels, sub-pixel (sh, sw)), which turns conv2's stride-2 taps into shifts by whole
+// cells: tap kh -> (dh, sh) = (-1,1),(0,0),(0,1), same for kw. Two buffers per unit, each 9 cell rows (1 halo + 8) x
+// 16 cells x 128 B (64 channels = both sub-rows sh of one sub-column sw):
+//   AL0: sw = 0, K order [sh=0 | sh=1]  -> taps kw = 1
+//   AL1: sw = 1, K order [sh=1 | sh=0]  -> taps kw = 2, and taps kw = 0 of the cell to the RIGHT
+// (the opposite K orders make the two pixels a quarter-warp stores land in different bank halves).
 // A dh=-1 tap is the same buffer addressed one cell row (16 rows = 2 swizzle atoms) higher, so every UMMA descriptor
-// stays atom-aligned. K = 3 buffers x (4 K-steps for dh=0 + 2 K-steps (sh=1 only) for dh=-1) x 16 = 288 = 9*32: no
-// padded K at all. The 18 dependent UMMAs of a unit alternate between two accumulators (split-K) that the epilogue adds.
+// stays atom-aligned. The kw = 0 taps need the cell to the LEFT, a one-row shift that a swizzled descriptor cannot
+// express; instead they accumulate UNSHIFTED into their own accumulators and the epilogue adds row r-1 into row r
+// (one warp shuffle; cell column 0 gets the zero padding). K = 288 real, no padded K at all; the 18 K-steps of a unit
+// rotate over four accumulators (2 regular + 2 shifted, summed by the epilogue) because UMMAs into the same TMEM tile
+// only issue every ~180 cycles, far longer than a 128x64x16 instruction needs.
+//
+// A producer task = two vertically adjacent conv1 output rows x 16 columns (= one cell row x 8 cells, both sh): the
+// 7 input rows they share are read once. Fragment rows are pixels ow0+g / ow0+g+8 and the conv1 weight columns are
+// permuted so that a thread ends up with 8 CONSECUTIVE channels of each of its pixels = one 16-byte store.
 #pragma once
 #include "conv1_kernel.cuh"
 #include "epilogues.cuh"
 
 namespace vfp {
 
-constexpr int kStemThreads = 960;
-constexpr int kStemProducerWarp0 = 6, kStemProducerWarps = 16;
-constexpr int kStemLoaderWarp0 = 22, kStemLoaderWarps = 8;
-constexpr int kStemC1WBytes = 5 * 4 * 32 * 8;      // conv1 B fragments: [kh][n-tile][lane] x 8 B
-constexpr int kStemABuf = 9 * 16 * 128;            // one of AL0 / AL1 / SH1: 18432 B
-constexpr int kStemUnitBytes = 3 * kStemABuf;      // 55296 B
-constexpr int kStemTileBytes = (kC1SmemElems * 2 + 127) / 128 * 128;
+constexpr int kStemThreads = 768;
+constexpr int kStemXposeWarp0 = 2, kStemXposeWarps = 2;
+constexpr int kStemEpiWarp0 = 4, kStemEpiWarps = 8;
+constexpr int kStemProdWarp0 = 12, kStemProdWarps = 12;
+constexpr int kStemTasks0 = 16, kStemTasks1 = 18;  // producer tasks of unit hf=0 / hf=1 (hf=1 recomputes the halo row pair)
+constexpr int kStemTasks = kStemTasks0 + kStemTasks1;
+constexpr int kStemABuf = 9 * 16 * 128;            // one of AL0 / AL1: 18432 B
+constexpr int kStemUnitBytes = 2 * kStemABuf;      // 36864 B
+constexpr int kStemWBlocks = 5;                    // conv2 weight K blocks of 64 (see vfp_weights_create)
+constexpr int kStemRawSlots = 5, kStemRawSlotBytes = 8192;
+// HWC tile: rows -2..64, 72 pixels per row (8 zero pixels, then columns 0..63; column 64 of a row IS the first zero
+// pixel of the next row), 3 channels interleaved: element ((h+2)*72 + w+8)*3 + c
+constexpr int kStemTilePitch = 72;
+constexpr int kStemTileBytes = 29184;
+static_assert((67 * kStemTilePitch + 8) * 6 <= kStemTileBytes, "HWC tile");
 
 struct StemSmem {
-  static constexpr int kC1 = 0;                                   // 2 units
-  static constexpr int kW = kC1 + 2 * kStemUnitBytes;             // 6 weight tiles of 64 rows x 128 B
-  static constexpr int kStage = kW + 6 * 8192;                    // 4 epilogue warps x 2 KB
-  static constexpr int kTile = kStage + 4 * 2048;                 // 2 frame tiles
-  static constexpr int kC1W = kTile + 2 * kStemTileBytes;
-  static constexpr int kBars = kC1W + kStemC1WBytes;
-  static constexpr int kTotal = kBars + 256 + 1024;
+  static constexpr int kC1 = 0;                                            // 2 units
+  static constexpr int kW = kC1 + 2 * kStemUnitBytes;                      // 5 weight tiles of 64 rows x 128 B
+  static constexpr int kStage = kW + kStemWBlocks * 8192;                  // 8 epilogue warps x 2 KB
+  static constexpr int kRaw = kStage + kStemEpiWarps * 2048;               // raw frame planes
+  static constexpr int kTile = kRaw + kStemRawSlots * kStemRawSlotBytes;   // 2 HWC tiles
+  static constexpr int kBars = kTile + 2 * kStemTileBytes;
+  static constexpr int kTotal = kBars + 512 + 1024;
 };
 static_assert(StemSmem::kTotal <= 232448, "stem kernel shared memory");
-static_assert(StemSmem::kW % 1024 == 0 && StemSmem::kStage % 1024 == 0, "swizzled regions must be 1024-byte aligned");
+static_assert(StemSmem::kW % 1024 == 0 && StemSmem::kStage % 1024 == 0 && StemSmem::kRaw % 1024 == 0, "alignment");
 
 struct StemParams {
-  alignas(64) CUtensorMap tmap_w;    // conv2 weights [64][384] bf16 (fused K order), box 64 rows x 64 K, SWIZZLE_128B
+  alignas(64) CUtensorMap tmap_w;    // conv2 weights [64][320] bf16 (fused K order), box 64 rows x 64 K, SWIZZLE_128B
   alignas(64) CUtensorMap tmap_out;  // conv2 output [frames*256][64] bf16, box 32 x 32, SWIZZLE_64B
-  const void* frames;
+  const void* frames;                // planar u8 / planar bf16 / decoder-layout u8, 16-byte aligned
   int frame_dtype;
   long long n_frames;
-  const uint32_t* c1_wpack;  // conv1 B fragments
-  const float* c1_bias;
+  const uint32_t* c1_wpack;  // conv1 B fragments, output channels permuted (column n of tile nt = channel 8*(n>>1) + 2*nt + (n&1))
+  const float* c1_bias;      // [32] natural channel order
   const float* c2_bias;
 };
 
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+// relu + round to bf16 of two floats in one instruction; `lo` lands in the low half
+__device__ __forceinline__ uint32_t relu_pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// u8 -> value/255 as bf16 pairs
+__device__ __forceinline__ uint32_t u8x2_to_bf16x2(uint32_t lo, uint32_t hi) {
+  return pack_bf16x2((float)lo * (1.0f / 255.0f), (float)hi * (1.0f / 255.0f));
+}
+
 __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __grid_constant__ StemParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // keep the pointer arithmetic on the __shared__ array (no integer round trip) so accesses compile to LDS / STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* c1buf = smem + StemSmem::kC1;
   uint8_t* wbuf = smem + StemSmem::kW;
   uint8_t* stagebuf = smem + StemSmem::kStage;
+  uint8_t* rawbuf = smem + StemSmem::kRaw;
+  uint8_t* tilebuf = smem + StemSmem::kTile;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + StemSmem::kBars);
   uint64_t* w_full = bars;            // [1]
-  uint64_t* c1_full = bars + 1;       // [2] producers -> UMMA
+  uint64_t* c1_full = bars + 1;       // [2] producers -> UMMA (one arrive per producer task)
   uint64_t* c1_empty = bars + 3;      // [2] UMMA -> producers
   uint64_t* acc_full = bars + 5;      // [2] UMMA -> epilogue
   uint64_t* acc_empty = bars + 7;     // [2] epilogue -> UMMA
-  uint64_t* tile_full = bars + 9;     // [2] loaders -> producers
-  uint64_t* tile_empty = bars + 11;   // [2] producers -> loaders
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* tile_full = bars + 9;     // [2] transposers -> producers
+  uint64_t* tile_empty = bars + 11;   // [2] producers -> transposers
+  uint64_t* raw_full = bars + 13;     // [5] bulk copy -> transposers
+  uint64_t* raw_empty = bars + 18;    // [5] transposers -> bulk copy issuer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   // frames of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
   const long long n_local = (p.n_frames > blockIdx.x) ? (p.n_frames - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  // zero everything that is read before it is written: c1 halo rows / SH1 column 0, the tile halos
+  // zero everything that is read before it is written: the c1 halo row blocks, the tile halos
   for (int i = tid; i < (2 * kStemUnitBytes) / 16; i += kStemThreads) reinterpret_cast<uint4*>(c1buf)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < (2 * kStemTileBytes) / 16; i += kStemThreads) reinterpret_cast<uint4*>(smem + StemSmem::kTile)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < kStemC1WBytes / 8; i += kStemThreads)
-    reinterpret_cast<uint2*>(smem + StemSmem::kC1W)[i] = __ldg(reinterpret_cast<const uint2*>(p.c1_wpack) + i);
+  for (int i = tid; i < (2 * kStemTileBytes) / 16; i += kStemThreads) reinterpret_cast<uint4*>(tilebuf)[i] = make_uint4(0, 0, 0, 0);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_w);
     tma_prefetch_desc(&p.tmap_out);
     mbar_init(w_full, 1);
+    mbar_init(&c1_full[0], kStemTasks0);
+    mbar_init(&c1_full[1], kStemTasks1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&c1_full[i], kStemProducerWarps);
       mbar_init(&c1_empty[i], 1);
       mbar_init(&acc_full[i], 1);
-      mbar_init(&acc_empty[i], 4);
-      mbar_init(&tile_full[i], kStemLoaderWarps);
-      mbar_init(&tile_empty[i], kStemProducerWarps);
+      mbar_init(&acc_empty[i], kStemEpiWarps);
+      mbar_init(&tile_full[i], kStemXposeWarps);
+      mbar_init(&tile_empty[i], kStemProdWarps);
+    }
+    for (int i = 0; i < kStemRawSlots; ++i) {
+      mbar_init(&raw_full[i], 1);
+      mbar_init(&raw_empty[i], kStemXposeWarps);
     }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 256);  // 2 units x 2 split-K accumulators x 64 columns
+    tmem_alloc(tmem_slot, 512);  // 2 units x 4 accumulators x 64 columns
     tmem_relinquish();
   }
   fence_proxy_async_smem();  // the zero fill is read by the UMMA (async proxy)
@@ -108,188 +150,312 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const bool is_bf16 = p.frame_dtype == kFrameBF16;
+  const uint32_t plane_bytes = is_bf16 ? 8192u : 4096u;  // a third of a frame (for decoder-layout u8: just a chunk)
 
-  if (warp == 0) {
-    // ------------------------------ conv2 weights, once ------------------------------
-    if (lane == 0) {
-      mbar_arrive_expect_tx(w_full, 6 * 8192);
-      for (int kb = 0; kb < 6; ++kb) tma_load_2d(&p.tmap_w, w_full, wbuf + kb * 8192, kb * 64, 0);
-    }
-  } else if (warp == 1) {
-    // ------------------------------ UMMA issuer ------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
-      mbar_wait(w_full, 0);
-      for (long long u = 0; u < 2 * n_local; ++u) {
-        const int b = (int)(u & 1);
-        const uint32_t ph = (uint32_t)((u >> 1) & 1);
-        mbar_wait(&acc_empty[b], ph ^ 1);
-        mbar_wait(&c1_full[b], ph);
-        tc_fence_after();
-        const uint32_t a_base = smem_u32(c1buf + b * kStemUnitBytes);
-        const uint32_t w_base = smem_u32(wbuf);
-        const uint32_t d_base = tmem_base + b * 128;
-        int step = 0;
-#pragma unroll
-        for (int dh = 0; dh >= -1; --dh) {
-#pragma unroll
-          for (int x = 0; x < 3; ++x) {
-            // dh = 0: rows start one cell row (16 rows) below the halo row, all 4 K-steps; dh = -1: from the halo row,
-            // only the sh = 1 half of the 64 channels (K-steps 2, 3)
-            const uint64_t adesc = umma_smem_desc_kmajor<128>(a_base + x * kStemABuf + (dh == 0 ? 16 * 128 : 0));
-            const uint64_t bdesc = umma_smem_desc_kmajor<128>(w_base + ((dh == 0 ? 0 : 3) + x) * 8192);
-#pragma unroll
-            for (int k = (dh == 0 ? 0 : 2); k < 4; ++k, ++step)
-              umma_bf16(d_base + (step & 1) * 64, adesc + 2 * k, bdesc + 2 * k, idesc, step >= 2 ? 1u : 0u);
+  // setmaxnreg re-balances inside the CTA's own allocation (768 threads x 80 registers = 480 per warpgroup-thread):
+  // 56 + 2*56 + 3*104 = 480. An inc that the decs do not cover blocks forever.
+  if (warp < kStemEpiWarp0) {
+    setmaxnreg_dec<56>();
+    if (warp == 0) {
+      // ------------------------------ weights once, then the raw-plane ring ------------------------------
+      if (lane == 0) {
+        mbar_arrive_expect_tx(w_full, kStemWBlocks * 8192);
+        for (int kb = 0; kb < kStemWBlocks; ++kb) tma_load_2d(&p.tmap_w, w_full, wbuf + kb * 8192, kb * 64, 0);
+        const uint8_t* base = static_cast<const uint8_t*>(p.frames);
+        int slot = 0;
+        uint32_t ph = 0;
+        for (long long li = 0; li < n_local; ++li) {
+          const uint8_t* src = base + (size_t)(blockIdx.x + li * gridDim.x) * (3 * plane_bytes);
+          for (int c = 0; c < 3; ++c) {
+            mbar_wait_relaxed(&raw_empty[slot], ph ^ 1);
+            mbar_arrive_expect_tx(&raw_full[slot], plane_bytes);
+            bulk_copy_g2s(rawbuf + slot * kStemRawSlotBytes, src + c * plane_bytes, plane_bytes, &raw_full[slot]);
+            if (++slot == kStemRawSlots) { slot = 0; ph ^= 1; }
           }
         }
-        umma_commit(&c1_empty[b]);
-        umma_commit(&acc_full[b]);
+      }
+    } else if (warp == 1) {
+      // ------------------------------ UMMA issuer ------------------------------
+      if (lane == 0) {
+        constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+        mbar_wait_relaxed(w_full, 0);
+        const uint32_t w_base = smem_u32(wbuf);
+        for (long long u = 0; u < 2 * n_local; ++u) {
+          const int b = (int)(u & 1);
+          const uint32_t ph = (uint32_t)((u >> 1) & 1);
+          mbar_wait_relaxed(&acc_empty[b], ph ^ 1);
+          mbar_wait_relaxed(&c1_full[b], ph);
+          tc_fence_after();
+          const uint32_t al0 = smem_u32(c1buf + b * kStemUnitBytes), al1 = al0 + kStemABuf;
+          const uint32_t d_base = tmem_base + b * 256;
+          // (A buffer, first A K-step, weight block, first weight K-step, K-steps, shifted?) per tap group
+          //   G_A AL0 dh=0  kw=1 | G_B AL1 dh=0 kw=2 | G_C AL1 dh=0 kw=0 (shifted)
+          //   G_D AL0 dh=-1 kw=1 (sh=1 = K-steps 2,3) | G_E AL1 dh=-1 kw=2 (K-steps 0,1) | G_F AL1 dh=-1 kw=0 (shifted)
+          // the issue order interleaves the groups so that consecutive UMMAs hit different accumulators
+          auto issue = [&](uint32_t a_addr, int ka, int wblk, int kb, int acc, uint32_t accumulate) {
+            const uint64_t adesc = umma_smem_desc_kmajor<128>(a_addr) + 2 * ka;
+            const uint64_t bdesc = umma_smem_desc_kmajor<128>(w_base + wblk * 8192) + 2 * kb;
+            umma_bf16(d_base + acc * 64, adesc, bdesc, idesc, accumulate);
+          };
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            issue(al0 + 2048, k, 0, k, 0, k > 0);            // G_A -> acc 0
+            issue(al1 + 2048, k, 1, k, 1, k > 0);            // G_B -> acc 1
+            issue(al1 + 2048, k, 2, k, 2 + (k & 1), k > 1);  // G_C -> acc 2 / 3
+          }
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            issue(al0, 2 + k, 3, k, 0, 1);      // G_D -> acc 0
+            issue(al1, k, 3, 2 + k, 1, 1);      // G_E -> acc 1
+            issue(al1, k, 4, k, 2 + k, 1);      // G_F -> acc 2 / 3
+          }
+          umma_commit(&c1_empty[b]);
+          umma_commit(&acc_full[b]);
+        }
+      }
+    } else {
+      // ------------------------------ transposers: raw planes -> HWC tile ------------------------------
+      const int ltid = tid - kStemXposeWarp0 * 32;
+      constexpr int kXThreads = kStemXposeWarps * 32;
+      int slot0 = 0;       // ring slot of plane 0 of the current frame
+      uint32_t n0 = 0;     // plane sequence number of plane 0 of the current frame
+      for (long long li = 0; li < n_local; ++li) {
+        const int t = (int)(li & 1);
+        uint8_t* tile = tilebuf + t * kStemTileBytes;
+        mbar_wait_relaxed(&tile_empty[t], (uint32_t)(((li >> 1) & 1) ^ 1));
+        const uint8_t* pl[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const uint32_t n = n0 + c;
+          const int s = (slot0 + c) % kStemRawSlots;
+          mbar_wait_relaxed(&raw_full[s], (n / kStemRawSlots) & 1u);
+          pl[c] = rawbuf + s * kStemRawSlotBytes;
+        }
+        if (is_bf16) {
+          // item = 8 pixels of one row: 3 x 16 B in (one per plane), 48 contiguous bytes out
+          for (int i = ltid; i < 512; i += kXThreads) {
+            const int h = i >> 3, w0 = (i & 7) * 8;
+            const uint4 a = *reinterpret_cast<const uint4*>(pl[0] + (h * 64 + w0) * 2);
+            const uint4 b = *reinterpret_cast<const uint4*>(pl[1] + (h * 64 + w0) * 2);
+            const uint4 c = *reinterpret_cast<const uint4*>(pl[2] + (h * 64 + w0) * 2);
+            uint4* dst = reinterpret_cast<uint4*>(tile + (h + 2) * (kStemTilePitch * 6) + (w0 + 8) * 6);
+            // words of the HWC stream: (a0 b0)(c0 a1)(b1 c1) (a2 b2)(c2 a3)(b3 c3) ...
+            uint4 o0, o1, o2;
+            o0.x = __byte_perm(a.x, b.x, 0x5410); o0.y = __byte_perm(c.x, a.x, 0x7610); o0.z = __byte_perm(b.x, c.x, 0x7632);
+            o0.w = __byte_perm(a.y, b.y, 0x5410); o1.x = __byte_perm(c.y, a.y, 0x7610); o1.y = __byte_perm(b.y, c.y, 0x7632);
+            o1.z = __byte_perm(a.z, b.z, 0x5410); o1.w = __byte_perm(c.z, a.z, 0x7610); o2.x = __byte_perm(b.z, c.z, 0x7632);
+            o2.y = __byte_perm(a.w, b.w, 0x5410); o2.z = __byte_perm(c.w, a.w, 0x7610); o2.w = __byte_perm(b.w, c.w, 0x7632);
+            dst[0] = o0; dst[1] = o1; dst[2] = o2;
+          }
+        } else if (p.frame_dtype == kFrameU8) {
+          for (int i = ltid; i < 512; i += kXThreads) {
+            const int h = i >> 3, w0 = (i & 7) * 8;
+            const uint2 a = *reinterpret_cast<const uint2*>(pl[0] + h * 64 + w0);
+            const uint2 b = *reinterpret_cast<const uint2*>(pl[1] + h * 64 + w0);
+            const uint2 c = *reinterpret_cast<const uint2*>(pl[2] + h * 64 + w0);
+            uint4* dst = reinterpret_cast<uint4*>(tile + (h + 2) * (kStemTilePitch * 6) + (w0 + 8) * 6);
+            uint32_t o[12];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const uint32_t av = half ? a.y : a.x, bv = half ? b.y : b.x, cv = half ? c.y : c.x;
+#pragma unroll
+              for (int pp = 0; pp < 2; ++pp) {  // pixel pair (2pp, 2pp+1) of this half
+                const uint32_t a0 = (av >> (16 * pp)) & 0xFF, a1 = (av >> (16 * pp + 8)) & 0xFF;
+                const uint32_t b0 = (bv >> (16 * pp)) & 0xFF, b1 = (bv >> (16 * pp + 8)) & 0xFF;
+                const uint32_t c0 = (cv >> (16 * pp)) & 0xFF, c1 = (cv >> (16 * pp + 8)) & 0xFF;
+                o[half * 6 + pp * 3 + 0] = u8x2_to_bf16x2(a0, b0);
+                o[half * 6 + pp * 3 + 1] = u8x2_to_bf16x2(c0, a1);
+                o[half * 6 + pp * 3 + 2] = u8x2_to_bf16x2(b1, c1);
+              }
+            }
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+          }
+        } else {
+          // decoder layout (H, W, 3) u8: the byte stream is already HWC; item = 16 bytes -> 32 bytes out
+          for (int i = ltid; i < 768; i += kXThreads) {
+            const int byte0 = i * 16;
+            const int chunk = byte0 >> 12;
+            const uint4 q = *reinterpret_cast<const uint4*>((chunk == 0 ? pl[0] : chunk == 1 ? pl[1] : pl[2]) + (byte0 & 4095));
+            const int h = byte0 / 192, off = byte0 - h * 192;
+            uint4* dst = reinterpret_cast<uint4*>(tile + (h + 2) * (kStemTilePitch * 6) + 48 + 2 * off);
+            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              o[2 * j] = u8x2_to_bf16x2(w[j] & 0xFF, (w[j] >> 8) & 0xFF);
+              o[2 * j + 1] = u8x2_to_bf16x2((w[j] >> 16) & 0xFF, w[j] >> 24);
+            }
+            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) mbar_arrive(&raw_empty[(slot0 + c) % kStemRawSlots]);
+          mbar_arrive(&tile_full[t]);
+        }
+        slot0 = (slot0 + 3) % kStemRawSlots;
+        n0 += 3;
       }
     }
-  } else if (warp < kStemProducerWarp0) {
+  } else if (warp < kStemProdWarp0) {
     // ------------------------------ conv2 epilogue ------------------------------
-    const int quarter = warp & 3;
-    uint8_t* dst = stagebuf + (warp - 2) * 2048;
+    setmaxnreg_dec<56>();
+    const int quarter = warp & 3;                      // TMEM lane quarter of this warp
+    const int col_half = (warp - kStemEpiWarp0) >> 2;  // 32 of the 64 output channels
+    uint8_t* dst = stagebuf + (warp - kStemEpiWarp0) * 2048;
+    uint8_t* r0 = dst + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    const bool first_cell = (lane & 15) == 0;  // cell column 0: the kw = 0 taps read the zero padding
     for (long long u = 0; u < 2 * n_local; ++u) {
       const int b = (int)(u & 1);
       const uint32_t ph = (uint32_t)((u >> 1) & 1);
       const long long frame = blockIdx.x + (u >> 1) * gridDim.x;
       mbar_wait_relaxed(&acc_full[b], ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + b * 128;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 64; c0 += 32) {
-        uint8_t* r0 = dst + lane * 64;
-        const int sw = (lane >> 1) & 3;
-        if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the staging tile
-        __syncwarp();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + b * 256 + col_half * 32;
+      if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the staging tile
+      __syncwarp();
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {  // 16 columns at a time keeps this role under 64 registers
-          uint32_t v0[16], v1[16];
-          tmem_ld_32x16(taddr + c0 + 16 * h, v0);
-          tmem_ld_32x16(taddr + 64 + c0 + 16 * h, v1);
-          tmem_ld_wait();
-          float x[16];
+      for (int c = 0; c < 4; ++c) {  // 8 columns (= one 16-byte staging chunk) at a time keeps this role under 56 registers
+        uint32_t v0[8], v1[8], v2[8], v3[8];
+        tmem_ld_32x8(taddr + 8 * c, v0);
+        tmem_ld_32x8(taddr + 64 + 8 * c, v1);
+        tmem_ld_32x8(taddr + 128 + 8 * c, v2);
+        tmem_ld_32x8(taddr + 192 + 8 * c, v3);
+        tmem_ld_wait();
+        uint32_t q[4];
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.c2_bias + c0 + 16 * h + i));
-            x[i] = fmaxf(__uint_as_float(v0[i]) + __uint_as_float(v1[i]) + bb.x, 0.0f);
-            x[i + 1] = fmaxf(__uint_as_float(v0[i + 1]) + __uint_as_float(v1[i + 1]) + bb.y, 0.0f);
-            x[i + 2] = fmaxf(__uint_as_float(v0[i + 2]) + __uint_as_float(v1[i + 2]) + bb.z, 0.0f);
-            x[i + 3] = fmaxf(__uint_as_float(v0[i + 3]) + __uint_as_float(v1[i + 3]) + bb.w, 0.0f);
+        for (int i = 0; i < 8; i += 4) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.c2_bias + col_half * 32 + 8 * c + i));
+          const float bias4[4] = {bb.x, bb.y, bb.z, bb.w};
+          float x[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float s = __uint_as_float(v2[i + j]) + __uint_as_float(v3[i + j]);
+            s = __shfl_up_sync(0xffffffffu, s, 1);
+            if (first_cell) s = 0.0f;
+            x[j] = __uint_as_float(v0[i + j]) + __uint_as_float(v1[i + j]) + bias4[j] + s;
           }
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            uint4 q;
-            q.x = pack_bf16x2(x[8 * c + 0], x[8 * c + 1]);
-            q.y = pack_bf16x2(x[8 * c + 2], x[8 * c + 3]);
-            q.z = pack_bf16x2(x[8 * c + 4], x[8 * c + 5]);
-            q.w = pack_bf16x2(x[8 * c + 6], x[8 * c + 7]);
-            *reinterpret_cast<uint4*>(r0 + (((2 * h + c) ^ sw) << 4)) = q;
-          }
+          q[i / 2] = relu_pack_bf16x2(x[0], x[1]);
+          q[i / 2 + 1] = relu_pack_bf16x2(x[2], x[3]);
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_2d(&p.tmap_out, dst, c0, (int)(frame * 256 + b * 128 + quarter * 32));
-          tma_store_commit();
-        }
+        *reinterpret_cast<uint4*>(r0 + ((c ^ sw) << 4)) = make_uint4(q[0], q[1], q[2], q[3]);
       }
       tc_fence_before();
+      fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[b]);
+      if (lane == 0) {
+        mbar_arrive(&acc_empty[b]);
+        tma_store_2d(&p.tmap_out, dst, col_half * 32, (int)(frame * 256 + b * 128 + quarter * 32));
+        tma_store_commit();
+      }
     }
     if (lane == 0) tma_store_wait_read<0>();
-  } else if (warp < kStemLoaderWarp0) {
+  } else {
     // ------------------------------ conv1 producers ------------------------------
-    const int pw = warp - kStemProducerWarp0;
+    setmaxnreg_inc<104>();
+    const int pw = warp - kStemProdWarp0;
     const int g = lane >> 2, tig = lane & 3;
-    const uint2* wfrag = reinterpret_cast<const uint2*>(smem + StemSmem::kC1W) + lane;  // [(kh*4+nt)*32 + lane]
+    uint32_t bfrag[5][4][2];
+#pragma unroll
+    for (int kh = 0; kh < 5; ++kh)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(p.c1_wpack) + (kh * 4 + nt) * 32 + lane);
+        bfrag[kh][nt][0] = w.x;
+        bfrag[kh][nt][1] = w.y;
+      }
+    // this thread's accumulator columns (2tig, 2tig+1) of n-tile nt are channels 8*tig + 2*nt, +1
     float bia[4][2];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      bia[nt][0] = __ldg(p.c1_bias + nt * 8 + 2 * tig);
-      bia[nt][1] = __ldg(p.c1_bias + nt * 8 + 2 * tig + 1);
+      bia[nt][0] = __ldg(p.c1_bias + 8 * tig + 2 * nt);
+      bia[nt][1] = __ldg(p.c1_bias + 8 * tig + 2 * nt + 1);
     }
-    for (long long li = 0; li < n_local; ++li) {
-      const int t = (int)(li & 1);
-      const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(smem + StemSmem::kTile + t * kStemTileBytes);
-      mbar_wait_relaxed(&tile_full[t], (uint32_t)((li >> 1) & 1));
-#pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        uint8_t* unit = c1buf + hf * kStemUnitBytes;
-        mbar_wait_relaxed(&c1_empty[hf], (uint32_t)((li & 1) ^ 1));
-        // conv1 output rows of this unit: hf = 0 -> 0..15 ; hf = 1 -> 14..31 (rows 14, 15 are the halo cell row,
-        // recomputed instead of shared with the other buffer). m-tile = one row x 16 columns.
-        const int row_first = hf == 0 ? 0 : 14;
-        const int n_mtiles = (hf == 0 ? 16 : 18) * 2;
-#pragma unroll 1
-        for (int mt = pw; mt < n_mtiles; mt += kStemProducerWarps) {
-          const int oh = row_first + (mt >> 1);
-          const int ow0 = (mt & 1) * 16;
-          float acc[4][4];
-#pragma unroll
-          for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[nt][i] = 0.0f;
-#pragma unroll
-          for (int kh = 0; kh < 5; ++kh) {
-            const int base_lo = (((2 * oh + kh) * kC1PadW + 2 * (ow0 + g)) * 3) >> 1;
-            const int base_hi = base_lo + 24;
-            uint32_t a[4];
-            a[0] = tile32[base_lo + tig];
-            a[1] = tile32[base_hi + tig];
-            a[2] = tile32[base_lo + tig + 4];
-            a[3] = tile32[base_hi + tig + 4];
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-              const uint2 wv = wfrag[(kh * 4 + nt) * 32];
-              const uint32_t bq[2] = {wv.x, wv.y};
-              mma_bf16_16816(acc[nt], a, bq);
-            }
-          }
-          // scatter into the A-operand buffers. pixel (oh, ow): cell (oh/2, ow/2), sub (sh, sw) = (oh%2, ow%2);
-          // buffer row = (cell_row - 8*hf + 1) * 16 + cell_col; 16-byte chunk j = sh*4 + nt, stored at j ^ (row % 8).
-          const int sh = oh & 1;
-          const int rowblk = (oh >> 1) - 8 * hf + 1;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int ow = ow0 + g + 8 * half;
-            const int cx = ow >> 1;
-            const int row = rowblk * 16 + cx;
-            uint8_t* al = unit + (ow & 1) * kStemABuf + row * 128 + tig * 4;
-            uint8_t* shf = unit + 2 * kStemABuf + (row + 1) * 128 + tig * 4;
-            const bool to_shift = (ow & 1) && cx < 15;
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-              const float v0 = fmaxf(acc[nt][2 * half] + bia[nt][0], 0.0f);
-              const float v1 = fmaxf(acc[nt][2 * half + 1] + bia[nt][1], 0.0f);
-              const uint32_t pk = pack_bf16x2(v0, v1);
-              const int j = sh * 4 + nt;
-              *reinterpret_cast<uint32_t*>(al + ((j ^ (row & 7)) << 4)) = pk;
-              if (to_shift) *reinterpret_cast<uint32_t*>(shf + ((j ^ ((row + 1) & 7)) << 4)) = pk;
-            }
-          }
+    // scatter constants: fragment row g = pixel ow0+g: sub-column sw = g & 1 (buffer AL0 / AL1), cell column (g >> 1);
+    // row g+8 = pixel ow0+g+8: same sub-column, 4 cells to the right. A buffer row's swizzle phase is (cell column) & 7.
+    const int psw = g & 1;
+    const int cxl = g >> 1;
+    const uint32_t ph_lo = (uint32_t)cxl, ph_hi = (uint32_t)(cxl + 4);
+    const int n_tasks = (int)(kStemTasks * n_local);  // a conv pass is at most 16384 frames
+    int cur_li = -1;
+    const uint32_t* tile32 = nullptr;
+
+    for (int tg = pw; tg < n_tasks; tg += kStemProdWarps) {
+      const int li = tg / kStemTasks;
+      const int task = tg - li * kStemTasks;
+      if (li != cur_li) {
+        if (cur_li >= 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tile_empty[cur_li & 1]);
         }
-        fence_proxy_async_smem();  // generic-proxy writes above -> visible to the UMMA reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&c1_full[hf]);
+        mbar_wait_relaxed(&tile_full[li & 1], (uint32_t)((li >> 1) & 1));
+        tile32 = reinterpret_cast<const uint32_t*>(tilebuf + (li & 1) * kStemTileBytes);
+        cur_li = li;
       }
+      const int hf = task >= kStemTasks0 ? 1 : 0;
+      const int tt = task - hf * kStemTasks0;
+      // cell row of this task: hf = 0 -> 0..7 ; hf = 1 -> 7..15 (cell row 7 is the halo row of the second unit)
+      const int cy = hf == 0 ? (tt >> 1) : 7 + (tt >> 1);
+      const int ow0 = (tt & 1) * 16;
+      uint8_t* unit = c1buf + hf * kStemUnitBytes;
+      mbar_wait_relaxed(&c1_empty[hf], (uint32_t)((li & 1) ^ 1));
+
+      float acc[2][4][4];
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          acc[s][nt][0] = bia[nt][0]; acc[s][nt][1] = bia[nt][1];
+          acc[s][nt][2] = bia[nt][0]; acc[s][nt][3] = bia[nt][1];
+        }
+      // output rows oh = 2*cy + s read tile rows 2*oh + kh = 4*cy + 2*s + kh: 7 distinct rows R = 0..6,
+      // row R feeds (s = 0, kh = R) and (s = 1, kh = R - 2). Word offset of (tile row r, pixel ow, k) =
+      // r*108 + 3*ow + 9 + k/2.
+      const uint32_t* trow = tile32 + (4 * cy) * 108 + 3 * (ow0 + g) + 9 + tig;
+#pragma unroll
+      for (int R = 0; R < 7; ++R) {
+        uint32_t a[4];
+        a[0] = trow[R * 108];
+        a[1] = trow[R * 108 + 24];
+        a[2] = trow[R * 108 + 4];
+        a[3] = trow[R * 108 + 28];
+        if (R <= 4) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[0][nt], a, bfrag[R <= 4 ? R : 0][nt]);
+        }
+        if (R >= 2) {
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) mma_bf16_16816(acc[1][nt], a, bfrag[R >= 2 ? R - 2 : 0][nt]);
+        }
+      }
+      // buffer row = (cy - 8*hf + 1) * 16 + cell column; 16-byte chunk (s ^ sw)*4 + tig stored at chunk ^ phase
+      const int rowblk = cy - 8 * hf + 1;
+      uint8_t* row_lo = unit + psw * kStemABuf + (rowblk * 16 + (ow0 >> 1) + cxl) * 128;
+      uint8_t* row_hi = row_lo + 4 * 128;
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const uint32_t chunk = (uint32_t)((s ^ psw) * 4 + tig);
+        uint4 lo, hi;
+        lo.x = relu_pack_bf16x2(acc[s][0][0], acc[s][0][1]); hi.x = relu_pack_bf16x2(acc[s][0][2], acc[s][0][3]);
+        lo.y = relu_pack_bf16x2(acc[s][1][0], acc[s][1][1]); hi.y = relu_pack_bf16x2(acc[s][1][2], acc[s][1][3]);
+        lo.z = relu_pack_bf16x2(acc[s][2][0], acc[s][2][1]); hi.z = relu_pack_bf16x2(acc[s][2][2], acc[s][2][3]);
+        lo.w = relu_pack_bf16x2(acc[s][3][0], acc[s][3][1]); hi.w = relu_pack_bf16x2(acc[s][3][2], acc[s][3][3]);
+        *reinterpret_cast<uint4*>(row_lo + ((chunk ^ ph_lo) << 4)) = lo;
+        *reinterpret_cast<uint4*>(row_hi + ((chunk ^ (ph_hi & 7)) << 4)) = hi;
+      }
+      fence_proxy_async_smem();  // generic-proxy writes above -> visible to the UMMA reads
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tile_empty[t]);
+      if (lane == 0) mbar_arrive(&c1_full[hf]);
     }
-  } else {
-    // ------------------------------ frame loaders ------------------------------
-    const int ltid = tid - kStemLoaderWarp0 * 32;
-    for (long long li = 0; li < n_local; ++li) {
-      const int t = (int)(li & 1);
-      mbar_wait_relaxed(&tile_empty[t], (uint32_t)(((li >> 1) & 1) ^ 1));
-      const long long frame = blockIdx.x + li * gridDim.x;
-      stage_frame_hwc(p.frames, p.frame_dtype, frame, reinterpret_cast<__nv_bfloat16*>(smem + StemSmem::kTile + t * kStemTileBytes), ltid,
-                      kStemLoaderWarps * 32);
+    if (cur_li >= 0) {
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tile_full[t]);
+      if (lane == 0) mbar_arrive(&tile_empty[cur_li & 1]);
     }
   }
 
@@ -298,7 +464,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 

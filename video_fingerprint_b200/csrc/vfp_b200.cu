@@ -109,6 +109,7 @@ struct vfp_weights {
   std::vector<void*> allocs;
   // frame encoder
   uint32_t* c1_wpack = nullptr;
+  uint32_t* c1_wpack_perm = nullptr;  // same fragments with the output channels permuted for the fused stem kernel
   float* c1_bias = nullptr;
   __nv_bfloat16 *c2_w = nullptr, *c3_w = nullptr, *c4_w = nullptr;
   float *c2_b = nullptr, *c3_b = nullptr, *c4_b = nullptr;
@@ -318,6 +319,13 @@ int vfp_device_sm_count(void) {
 int vfp_set_tuning(int key, long long value) {
   if (key == 0 && value >= 64) { g_stem_pass_frames = value; return 0; }
   if (key == 1) { g_fused_stem = value != 0; return 0; }
+  if (key == 2) {  // hang diagnosis: timed-out mbarrier waits are logged and abandoned instead of trapping
+    const int mode = value != 0;
+    const unsigned int zero = 0;
+    if (cudaMemcpyToSymbol(g_vfp_hang_mode, &mode, sizeof(mode)) != cudaSuccess) return 2;
+    if (cudaMemcpyToSymbol(g_vfp_hang_count, &zero, sizeof(zero)) != cudaSuccess) return 2;
+    return 0;
+  }
   return 1;
 }
 
@@ -345,6 +353,16 @@ unsigned int vfp_device_error_word(void) {
   cudaMemcpyFromSymbol(&v, g_vfp_device_error, sizeof(v));
   if (v) cudaMemcpyToSymbol(g_vfp_device_error, &zero, sizeof(zero));
   return v;
+}
+
+int vfp_debug_hang_log(unsigned int* out, int max_entries) {
+  unsigned int n = 0;
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(&n, g_vfp_hang_count, sizeof(n)) != cudaSuccess) return -1;
+  if (n > 64) n = 64;
+  if ((int)n > max_entries) n = (unsigned int)max_entries;
+  if (n && cudaMemcpyFromSymbol(out, g_vfp_hang_log, (size_t)n * 16) != cudaSuccess) return -1;
+  return (int)n;
 }
 
 void vfp_weights_destroy(vfp_weights* w) {
@@ -380,23 +398,26 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
       const int kw = k / 3, c = k % 3;
       return cw[((co * 3 + c) * 5 + kh) * 5 + kw] * bn.scale[co];
     };
-    std::vector<uint32_t> pack(5 * 4 * 32 * 2);
-    for (int kh = 0; kh < 5; ++kh)
-      for (int nt = 0; nt < 4; ++nt)
-        for (int lane = 0; lane < 32; ++lane) {
-          const int g = lane >> 2, tig = lane & 3, co = nt * 8 + g;
-          for (int r = 0; r < 2; ++r) {
-            const int k0 = 2 * tig + 8 * r;
-            const __nv_bfloat16 lo = __float2bfloat16(wk(co, kh, k0)), hi = __float2bfloat16(wk(co, kh, k0 + 1));
-            uint16_t l16, h16;
-            memcpy(&l16, &lo, 2);
-            memcpy(&h16, &hi, 2);
-            pack[((kh * 4 + nt) * 32 + lane) * 2 + r] = (uint32_t)l16 | ((uint32_t)h16 << 16);
+    // perm = 0: column g of n-tile nt is channel nt*8 + g (stand-alone conv1 kernel); perm = 1: channel
+    // 8*(g>>1) + 2*nt + (g&1), which leaves every thread of the fused stem kernel with 8 consecutive channels
+    std::vector<uint32_t> pack(5 * 4 * 32 * 2), pack_perm(5 * 4 * 32 * 2);
+    for (int perm = 0; perm < 2; ++perm)
+      for (int kh = 0; kh < 5; ++kh)
+        for (int nt = 0; nt < 4; ++nt)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, tig = lane & 3, co = perm ? 8 * (g >> 1) + 2 * nt + (g & 1) : nt * 8 + g;
+            for (int r = 0; r < 2; ++r) {
+              const int k0 = 2 * tig + 8 * r;
+              const __nv_bfloat16 lo = __float2bfloat16(wk(co, kh, k0)), hi = __float2bfloat16(wk(co, kh, k0 + 1));
+              uint16_t l16, h16;
+              memcpy(&l16, &lo, 2);
+              memcpy(&h16, &hi, 2);
+              (perm ? pack_perm : pack)[((kh * 4 + nt) * 32 + lane) * 2 + r] = (uint32_t)l16 | ((uint32_t)h16 << 16);
+            }
           }
-        }
     std::vector<float> bias(32);
     for (int co = 0; co < 32; ++co) bias[co] = cb[co] * bn.scale[co] + bn.shift[co];
-    if (upload(w, pack, &w->c1_wpack) || upload(w, bias, &w->c1_bias)) return bail("");
+    if (upload(w, pack, &w->c1_wpack) || upload(w, pack_perm, &w->c1_wpack_perm) || upload(w, bias, &w->c1_bias)) return bail("");
   }
   // ---- conv2..4 ----
   {  // conv2: K laid out to match kConv2KBlocks (see there)
@@ -417,18 +438,19 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
       bf[co] = cb[co] * bn.scale[co] + bn.shift[co];
     }
     if (upload(w, to_bf16(wf), &w->c2_w) || upload(w, bf, &w->c2_b)) return bail("");
-    // fused stem kernel (stem_fused_kernel.cuh): K block kb = (dh == 0 ? x : 3 + x), x = 0/1/2 <-> kw = 1/2/0,
-    // inside a block k = sh*32 + c with kh = 1 + sh for dh = 0, kh = 0 for (dh = -1, sh = 1), zero for (dh = -1, sh = 0)
-    std::vector<float> wfu((size_t)64 * 384, 0.0f);
-    const int kw_of_x[3] = {1, 2, 0};
+    // fused stem kernel (stem_fused_kernel.cuh), five K blocks of 64 = [half 0: 32 ch | half 1: 32 ch], per block and
+    // half the (kh, kw) tap it holds (-1 = zero):
+    //   blk0 G_A (AL0, dh=0):  (1,1) | (2,1)      blk1 G_B (AL1, dh=0): (2,2) | (1,2)      blk2 G_C (AL1, dh=0, shifted): (2,0) | (1,0)
+    //   blk3 G_D | G_E (dh=-1): (0,1) | (0,2)     blk4 G_F (dh=-1, shifted): (0,0) | zero
+    const int fused_tap[5][2][2] = {{{1, 1}, {2, 1}}, {{2, 2}, {1, 2}}, {{2, 0}, {1, 0}}, {{0, 1}, {0, 2}}, {{0, 0}, {-1, -1}}};
+    std::vector<float> wfu((size_t)64 * 320, 0.0f);
     for (int co = 0; co < 64; ++co)
-      for (int kb = 0; kb < 6; ++kb)
-        for (int sh = 0; sh < 2; ++sh) {
-          const int x = kb % 3, kw = kw_of_x[x];
-          const int kh = kb < 3 ? 1 + sh : (sh == 1 ? 0 : -1);
+      for (int kb = 0; kb < 5; ++kb)
+        for (int half = 0; half < 2; ++half) {
+          const int kh = fused_tap[kb][half][0], kw = fused_tap[kb][half][1];
           if (kh < 0) continue;
           for (int c = 0; c < 32; ++c)
-            wfu[(size_t)co * 384 + kb * 64 + sh * 32 + c] = cw[((co * 32 + c) * 3 + kh) * 3 + kw] * bn.scale[co];
+            wfu[(size_t)co * 320 + kb * 64 + half * 32 + c] = cw[((co * 32 + c) * 3 + kh) * 3 + kw] * bn.scale[co];
         }
     if (upload(w, to_bf16(wfu), &w->c2f_w)) return bail("");
   }
@@ -544,7 +566,7 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
     }
   }
   if (make_tmap_rows_bf16(&w->tm_c2, w->c2_w, 64, 384, 384, 64, 64) ||
-      make_tmap_rows_bf16(&w->tm_c2f, w->c2f_w, 64, 384, 384, 64, 64) ||
+      make_tmap_rows_bf16(&w->tm_c2f, w->c2f_w, 64, 320, 320, 64, 64) ||
       make_tmap_rows_bf16(&w->tm_c3, w->c3_w, 128, 576, 576, 128, 64) ||
       make_tmap_rows_bf16(&w->tm_c4, w->c4_w, 256, 1152, 1152, 256, 64) ||
       make_tmap_rows_bf16(&w->tm_tok, w->wtok, kDim, 256, 256, 256, 64) ||
@@ -576,12 +598,14 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
   // conv1 + conv2 can run in shorter "stem passes" (vfp_set_tuning key 0) so that conv1's output (64 KB per frame,
   // the largest tensor of the forward) is still in L2 when conv2 reads it; by default one stem pass = the conv pass.
   CUtensorMap ta;
-  if (g_fused_stem) {
+  // the fused stem streams raw frame planes with 16-byte bulk copies; fp32 frames (48 KB) do not fit its smem ring
+  const bool fused = g_fused_stem && frame_dtype != VFP_FRAME_F32 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0;
+  if (fused) {
     StemParams sp{};
     sp.tmap_w = w->tm_c2f;
     if (make_tmap_out(&sp.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (stem out)");
     sp.frames = frames; sp.frame_dtype = frame_dtype; sp.n_frames = F;
-    sp.c1_wpack = w->c1_wpack; sp.c1_bias = w->c1_bias; sp.c2_bias = w->c2_b;
+    sp.c1_wpack = w->c1_wpack_perm; sp.c1_bias = w->c1_bias; sp.c2_bias = w->c2_b;
     static bool configured = false;
     if (!configured) {
       VFP_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::kTotal));
@@ -592,7 +616,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     stem_fused_kernel<<<grid, kStemThreads, StemSmem::kTotal, st>>>(sp);
     g_prof.mark(kStConv2, st);  // the fused kernel is accounted under conv2; conv1 shows 0
   }
-  for (int64_t s0 = 0; s0 < F && !g_fused_stem; s0 += g_stem_pass_frames) {
+  for (int64_t s0 = 0; s0 < F && !fused; s0 += g_stem_pass_frames) {
     const int64_t n = std::min<int64_t>(g_stem_pass_frames, F - s0);
     g_prof.launches += 2;
     {
