@@ -221,8 +221,10 @@ def run_ours(args):
     lib = _native.load()
     if args.stem_pass:
         lib.vfp_set_tuning(0, args.stem_pass)
-    if args.fused_stem:
-        lib.vfp_set_tuning(1, 1)
+    if args.two_kernel_stem:
+        lib.vfp_set_tuning(1, 0)
+    if args.conv_pass:
+        lib.vfp_set_tuning(3, args.conv_pass)
     peaks = load_peaks()
 
     n_clips = args.clips
@@ -411,7 +413,8 @@ def main():
     ap.add_argument("--join-n", type=int, default=262_144)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--stem-pass", type=int, default=0, help="experiment: frames per conv1+conv2 stem pass")
-    ap.add_argument("--fused-stem", action="store_true", help="experiment: conv1+conv2 fused stem kernel")
+    ap.add_argument("--two-kernel-stem", action="store_true", help="experiment: stand-alone conv1 + conv2 kernels instead of the fused stem")
+    ap.add_argument("--conv-pass", type=int, default=0, help="experiment: frames per conv pass (<= 16384)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-join", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

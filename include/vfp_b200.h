@@ -117,9 +117,9 @@ const char* vfp_profile_stage_name(int i);
 int vfp_profile_read(double* stage_ms, int n_stages, uint64_t* launches, int reset);
 
 /* Tuning knobs for experiments (process-wide). key 0: frames per conv1+conv2 stem pass of the
- * unfused path (default 16384 = the conv pass, >= 64); key 1: 1 = fused conv1+conv2 stem kernel (experimental,
- * slower than the default two-kernel path in round 1), 0 = two kernels (default); key 2: 1 = hang diagnosis
- * mode (see vfp_debug_hang_log), 0 = watchdog traps (default). */
+ * unfused path (default 16384 = the conv pass, >= 64); key 1: 1 = fused conv1+conv2 stem kernel (default for
+ * u8 / bf16 frames), 0 = two kernels (always used for fp32 frames); key 2: 1 = hang diagnosis
+ * mode (see vfp_debug_hang_log), 0 = watchdog traps (default); key 3: frames per conv pass (64..16384, default 16384). */
 int vfp_set_tuning(int key, long long value);
 
 /* Reads and clears the device-side error word set by a kernel watchdog (0 = none). Synchronises. */

@@ -233,16 +233,17 @@ int prep_f32(vfp_weights* w, const float* src, size_t n, float** dev) {
 //   * the CONV region holds the activations of one "conv pass" (kConvPassFrames frames, 112 KB per frame): the
 //     frame encoder walks the token pass in such slices and only leaves the 512 B/frame pooled features behind.
 // ---------------------------------------------------------------------------------------------
-constexpr int64_t kConvPassFrames = 16384;
+constexpr int64_t kConvPassFrames = 16384;   // workspace is sized for this many frames per conv pass
+// frames actually walked per conv pass (vfp_set_tuning key 3, <= kConvPassFrames): a pass whose c2/c3 activations
+// (48 KB per frame) fit the 126 MB L2 lets conv3 / conv4 read them from L2 instead of HBM
+int64_t g_conv_pass_frames = kConvPassFrames;
 // conv1+conv2 sub-pass. Measured on B200 (10k x 64-frame clips): 512 -> 71.3 ms/step, 1024 -> 62.9, 2048 -> 60.7,
 // 4096 -> 58.9, 16384 -> 55.8: short L2-sized sub-passes lose more to small launches than they save in HBM traffic.
 int64_t g_stem_pass_frames = kConvPassFrames;
 // conv1+conv2 in one kernel (stem_fused_kernel.cuh: conv1's output stays in shared memory as conv2's UMMA operand).
-// Correct (tests/test_forward_gpu.py::test_fused_stem_matches) but measured SLOWER than the two HBM-bound kernels
-// (33.1 ms vs 13.4 + 12.9 ms per 10k clips): its 16 mma.sync producer warps are instruction-issue bound (~300
-// instructions per 16-pixel m-tile incl. the swizzled scatter). Kept behind vfp_set_tuning(1, 1) as the starting
-// point for the next round; the default stays on the two-kernel path.
-int g_fused_stem = 0;
+// Measured on B200 (10k x 64-frame clips): 18.4 ms vs 13.4 + 12.9 ms for the two HBM-bound kernels, so it is the
+// default for u8 / bf16 frames; vfp_set_tuning(1, 0) selects the two-kernel path (always used for fp32 frames).
+int g_fused_stem = 1;
 
 struct TokenWs {
   size_t cu, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, h, logits, xbf, pooled, pooled_bf, head_h, total;
@@ -319,6 +320,7 @@ int vfp_device_sm_count(void) {
 int vfp_set_tuning(int key, long long value) {
   if (key == 0 && value >= 64) { g_stem_pass_frames = value; return 0; }
   if (key == 1) { g_fused_stem = value != 0; return 0; }
+  if (key == 3 && value >= 64 && value <= kConvPassFrames) { g_conv_pass_frames = value; return 0; }
   if (key == 2) {  // hang diagnosis: timed-out mbarrier waits are logged and abandoned instead of trapping
     const int mode = value != 0;
     const unsigned int zero = 0;
@@ -710,8 +712,8 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   g_prof.mark(kStMisc, st);
 
   // ---- frame encoder, one conv pass at a time (frames are independent: slices ignore clip boundaries) ----
-  for (int64_t s0 = 0; s0 < F; s0 += kConvPassFrames) {
-    const int64_t n = std::min<int64_t>(kConvPassFrames, F - s0);
+  for (int64_t s0 = 0; s0 < F; s0 += g_conv_pass_frames) {
+    const int64_t n = std::min<int64_t>(g_conv_pass_frames, F - s0);
     if (int rc = encode_frames_pass(w, frames_base + (size_t)(f0 + s0) * frame_bytes, frame_dtype, n, feat + s0 * 256, conv_ws, st))
       return rc;
   }
