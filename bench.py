@@ -43,6 +43,7 @@ _T = T_FRAMES
 STAGE_FLOPS = {
     "conv1_stem": 2 * 1024 * 32 * 75 * _T,
     "conv2_igemm": 2 * 256 * 64 * 288 * _T,
+    "stem_fused": 2 * (1024 * 32 * 75 + 256 * 64 * 288) * _T,   # conv1 + conv2 in one kernel
     "conv3_igemm": 2 * 64 * 128 * 576 * _T,
     "conv4_igemm_pool": 2 * 16 * 256 * 1152 * _T,
     "token_embed_gemm": 2 * (256 * 128 + 128 * 256) * _T,
@@ -59,6 +60,7 @@ STAGE_FLOPS = {
 STAGE_BYTES = {
     "conv1_stem": (24576 + 65536) * _T,           # bf16 frame in, bf16 32x32x32 out
     "conv2_igemm": (65536 + 32768) * _T,          # conv1 output in, 16x16x64 out
+    "stem_fused": (24576 + 32768) * _T,           # bf16 frame in, 16x16x64 out (conv1's output never leaves the SM)
     "conv3_igemm": (32768 + 16384) * _T,
     "temporal_conv": 2 * (1024 + 1024) * _T,      # two blocks, fp32 stream in + out
     "layernorm": 8 * (1024 + 512 + 1024 + 512) * _T,
@@ -361,7 +363,7 @@ def run_ours(args):
     dom = max((k for k in stages if k in STAGE_FLOPS or k in STAGE_BYTES), key=lambda k: stages[k])
     token_passes = -(-n_clips * T_FRAMES // args.frames_per_pass)
     conv_passes = -(-min(n_clips * T_FRAMES, args.frames_per_pass) // 16384) * token_passes
-    launches_per_step = conv_passes if dom.startswith("conv") else token_passes * (4 if dom.endswith("gemm") or dom in ("attention", "mlp1_gemm_gelu") else 1)
+    launches_per_step = conv_passes if dom.startswith("conv") or dom == "stem_fused" else token_passes * (4 if dom.endswith("gemm") or dom in ("attention", "mlp1_gemm_gelu") else 1)
     dom_ms = stages[dom]
     tflops = STAGE_FLOPS.get(dom, 0) * n_clips / (dom_ms / 1000.0) / 1e12
     gbs = STAGE_BYTES.get(dom, 0) * n_clips / (dom_ms / 1000.0) / 1e9

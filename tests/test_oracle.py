@@ -125,3 +125,23 @@ def test_oracle_against_live_reference():
             got = forward_oracle(sd, clip.unsqueeze(0), st)
             assert torch.allclose(got, want, atol=2e-6)
             assert torch.allclose(st["attn3"], feats, atol=1e-4, rtol=1e-5)
+
+
+def test_tanh_gelu_is_harmless():
+    """The CUDA MLP epilogue evaluates GELU in its tanh form (csrc/epilogues.cuh). Pin the claim made there: swapping
+    the exact erf form for the tanh form in the fp32 oracle moves the embeddings by far less than the parity bar."""
+    import torch.nn.functional as F
+
+    import oracle.forward_oracle as fo
+
+    sd = make_state_dict(2, "stress")
+    clips = make_clips(41, [37, 64, 10, 21], "colour")
+    exact = torch.stack(fo.fingerprint_clips(sd, clips)).double()
+    orig = F.gelu
+    try:
+        fo.F.gelu = lambda h: orig(h, approximate="tanh")
+        approx = torch.stack(fo.fingerprint_clips(sd, clips)).double()
+    finally:
+        fo.F.gelu = orig
+    cos = (exact * approx).sum(-1) / (exact.norm(dim=-1) * approx.norm(dim=-1))
+    assert float((1 - cos).max()) < 1e-7

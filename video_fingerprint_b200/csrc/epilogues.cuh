@@ -5,19 +5,18 @@
 
 namespace vfp {
 
-// Exact (erf-form) GELU, nn.GELU() default (model.py:136). erf via Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7,
-// far below the bf16 rounding of the stored activation): one exp, one reciprocal and a 5-term Horner chain instead of
-// erff's long polynomial - the MLP up-projection epilogue evaluates 2.6e9 of these per 10k clips on 8 warps per SM.
+// GELU of the MLP up-projection (nn.GELU() default = erf form, model.py:136). The epilogue evaluates 2.6e9 of these per
+// 10k clips and is issue-bound on them (the erf form costs ~18 instructions and two MUFU ops per value), so the
+// value is computed as 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) with the hardware tanh (one MUFU op, six
+// instructions). |difference to the erf form| <= 4.8e-4 (+ 2^-11 relative from tanh.approx), below the bf16 rounding
+// the stored activation gets anyway for |x| > 0.1; measured end to end on the fp32 oracle the embeddings move by
+// 1 - cos = 2e-9 (tests/test_oracle.py::test_tanh_gelu_is_harmless).
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  const float erfc_z = p * t * __expf(-z * z);     // 1 - erf(|x|/sqrt2)
-  const float half_erfc = 0.5f * erfc_z;
-  return x >= 0.0f ? x * (1.0f - half_erfc) : x * half_erfc;
+  const float u = x * fmaf(x * x, 0.0356774081f, 0.7978845608f);
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+  const float hx = 0.5f * x;
+  return fmaf(hx, t, hx);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -22,9 +22,10 @@
 // A dh=-1 tap is the same buffer addressed one cell row (16 rows = 2 swizzle atoms) higher, so every UMMA descriptor
 // stays atom-aligned. The kw = 0 taps need the cell to the LEFT, a one-row shift that a swizzled descriptor cannot
 // express; instead they accumulate UNSHIFTED into their own accumulators and the epilogue adds row r-1 into row r
-// (one warp shuffle; cell column 0 gets the zero padding). K = 288 real, no padded K at all; the 18 K-steps of a unit
-// rotate over four accumulators (2 regular + 2 shifted, summed by the epilogue) because UMMAs into the same TMEM tile
-// only issue every ~180 cycles, far longer than a 128x64x16 instruction needs.
+// (one warp shuffle; cell column 0 gets the zero padding). K = 288 real, no padded K at all. The kw = 2 and kw = 0
+// taps read the SAME A rows (AL1), so each such pair is ONE N = 128 UMMA against the stacked weights [W_kw2 ; W_kw0]
+// (columns 0-63 regular, 64-127 shifted): an SS-mode M128 K16 UMMA costs ~49 cycles at N = 64 but only ~65 at
+// N = 128 (tests/cuda/microbench_tensor.cu), so a unit takes 12 UMMAs / ~690 cycles instead of 18 / ~880.
 //
 // A producer task = two vertically adjacent conv1 output rows x 16 columns (= one cell row x 8 cells, both sh): the
 // 7 input rows they share are read once. Fragment rows are pixels ow0+g / ow0+g+8 and the conv1 weight columns are
@@ -142,7 +143,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 512);  // 2 units x 4 accumulators x 64 columns
+    tmem_alloc(tmem_slot, 512);  // 2 units x 192 accumulator columns
     tmem_relinquish();
   }
   fence_proxy_async_smem();  // the zero fill is read by the UMMA (async proxy)
@@ -188,27 +189,28 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
           mbar_wait_relaxed(&c1_full[b], ph);
           tc_fence_after();
           const uint32_t al0 = smem_u32(c1buf + b * kStemUnitBytes), al1 = al0 + kStemABuf;
-          const uint32_t d_base = tmem_base + b * 256;
-          // (A buffer, first A K-step, weight block, first weight K-step, K-steps, shifted?) per tap group
-          //   G_A AL0 dh=0  kw=1 | G_B AL1 dh=0 kw=2 | G_C AL1 dh=0 kw=0 (shifted)
-          //   G_D AL0 dh=-1 kw=1 (sh=1 = K-steps 2,3) | G_E AL1 dh=-1 kw=2 (K-steps 0,1) | G_F AL1 dh=-1 kw=0 (shifted)
-          // the issue order interleaves the groups so that consecutive UMMAs hit different accumulators
-          auto issue = [&](uint32_t a_addr, int ka, int wblk, int kb, int acc, uint32_t accumulate) {
+          const uint32_t d_base = tmem_base + b * 192;
+          // accumulator R (columns 0-63): kw = 1 taps; accumulator M (columns 64-191): kw = 2 taps in its first 64
+          // columns, kw = 0 taps (to be shifted by the epilogue) in its last 64.
+          //   G_A  AL0 dh=0  kw=1 (4 K-steps)            -> R     weights blk0
+          //   G_BC AL1 dh=0  kw=2|0 (4 K-steps, N=128)   -> M     weights blk1 ; blk2 (stacked)
+          //   G_D  AL0 dh=-1 kw=1 (sh=1 = A K-steps 2,3) -> R     weights blk3 K-steps 2,3
+          //   G_EF AL1 dh=-1 kw=2|0 (A K-steps 0,1, N=128) -> M   weights blk3 ; blk4 K-steps 0,1 (stacked)
+          constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
+          auto issue = [&](uint32_t a_addr, int ka, int wblk, int kb, bool wide, uint32_t accumulate) {
             const uint64_t adesc = umma_smem_desc_kmajor<128>(a_addr) + 2 * ka;
             const uint64_t bdesc = umma_smem_desc_kmajor<128>(w_base + wblk * 8192) + 2 * kb;
-            umma_bf16(d_base + acc * 64, adesc, bdesc, idesc, accumulate);
+            umma_bf16(d_base + (wide ? 64 : 0), adesc, bdesc, wide ? idesc128 : idesc, accumulate);
           };
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            issue(al0 + 2048, k, 0, k, 0, k > 0);            // G_A -> acc 0
-            issue(al1 + 2048, k, 1, k, 1, k > 0);            // G_B -> acc 1
-            issue(al1 + 2048, k, 2, k, 2 + (k & 1), k > 1);  // G_C -> acc 2 / 3
+            issue(al0 + 2048, k, 0, k, false, k > 0);   // G_A
+            issue(al1 + 2048, k, 1, k, true, k > 0);    // G_BC
           }
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
-            issue(al0, 2 + k, 3, k, 0, 1);      // G_D -> acc 0
-            issue(al1, k, 3, 2 + k, 1, 1);      // G_E -> acc 1
-            issue(al1, k, 4, k, 2 + k, 1);      // G_F -> acc 2 / 3
+            issue(al0, 2 + k, 3, 2 + k, false, 1);      // G_D
+            issue(al1, k, 3, k, true, 1);               // G_EF
           }
           umma_commit(&c1_empty[b]);
           umma_commit(&acc_full[b]);
@@ -317,16 +319,15 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
       const long long frame = blockIdx.x + (u >> 1) * gridDim.x;
       mbar_wait_relaxed(&acc_full[b], ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + b * 256 + col_half * 32;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + b * 192 + col_half * 32;
       if (lane == 0) tma_store_wait_read<0>();  // the previous store has finished reading the staging tile
       __syncwarp();
 #pragma unroll
       for (int c = 0; c < 4; ++c) {  // 8 columns (= one 16-byte staging chunk) at a time keeps this role under 56 registers
-        uint32_t v0[8], v1[8], v2[8], v3[8];
-        tmem_ld_32x8(taddr + 8 * c, v0);
-        tmem_ld_32x8(taddr + 64 + 8 * c, v1);
-        tmem_ld_32x8(taddr + 128 + 8 * c, v2);
-        tmem_ld_32x8(taddr + 192 + 8 * c, v3);
+        uint32_t v0[8], v1[8], v2[8];
+        tmem_ld_32x8(taddr + 8 * c, v0);         // kw = 1 taps
+        tmem_ld_32x8(taddr + 64 + 8 * c, v1);    // kw = 2 taps
+        tmem_ld_32x8(taddr + 128 + 8 * c, v2);   // kw = 0 taps of the cell to the left
         tmem_ld_wait();
         uint32_t q[4];
 #pragma unroll
@@ -336,8 +337,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
           float x[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            float s = __uint_as_float(v2[i + j]) + __uint_as_float(v3[i + j]);
-            s = __shfl_up_sync(0xffffffffu, s, 1);
+            float s = __shfl_up_sync(0xffffffffu, __uint_as_float(v2[i + j]), 1);
             if (first_cell) s = 0.0f;
             x[j] = __uint_as_float(v0[i + j]) + __uint_as_float(v1[i + j]) + bias4[j] + s;
           }

@@ -112,52 +112,101 @@ add_convert_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__
 
 // ---------------------------------------------------------------------------------------------
 // TemporalConvBlock + residual:  y = x + relu(bn(groupedconv_k(x)))  for k in {3,5,7,11} concatenated.
-// Output channel o (branch o/64, group o%64) reads input channels 4*(o%64) .. +3 (model.py:163-169).
-// Weights are BN-folded and zero-padded to 11 centred taps: w[ci][tap][o], so all 256 channels run the
-// same loop and weight reads are coalesced.
+// Output channel o (branch o/64, group o%64) reads input channels 4*(o%64) .. +3 (model.py:163-169), so the four
+// branches of group g share one 4-channel input window. Thread = group g of one token stream; it produces the
+// group's 4 outputs (one per branch) with the REAL tap counts 3/5/7/11 = 104 FMAs per token - no padded taps, and
+// the input is read once instead of once per branch. FOUR consecutive tokens are processed together, tap-major:
+// per tap the (at most 4) weight vectors of the group are read once from shared memory (one float4 = the 4 input
+// channels, BN folded) and one new input row enters a 4-row register window, so 4 tokens cost 14 row loads and 26
+// weight loads for 416 FMAs. Tokens of all clips are packed; a per-token 11-bit mask says which taps stay inside
+// the token's own clip (zero padding of Conv1d(padding=k//2) on a B=1 clip); token quads whose masks are all-ones
+// (the interior of a clip) take a predicate-free path.
 // ---------------------------------------------------------------------------------------------
+constexpr int kTcTok = 32;  // tokens per stream (a multiple of 4); a 256-thread CTA runs four streams
+
+template <bool kMasked>
+__device__ __forceinline__ void temporal_conv_quad(const float* __restrict__ x, const float4 (*ws)[64], int g, int t, int n_tokens,
+                                                   const unsigned (&mask)[4], float (&acc)[4][4]) {
+  // rows[q] = x[t - 5 + tap + q][4g .. 4g+3] while tap is processed; rows outside the packed buffer are never used
+  // by a valid tap, they are only kept from being dereferenced
+  auto load_row = [&](int r) -> float4 {
+    return (r >= 0 && r < n_tokens) ? *reinterpret_cast<const float4*>(x + (size_t)r * kDim + 4 * g) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 rows[4];
+  rows[0] = load_row(t - 5);
+  rows[1] = load_row(t - 4);
+  rows[2] = load_row(t - 3);
+#pragma unroll
+  for (int tap = 0; tap < 11; ++tap) {
+    rows[(tap + 3) & 3] = load_row(t - 2 + tap);
+    const float4 w3 = ws[15 + tap][g];
+    float4 w2 = w3, w1 = w3, w0 = w3;
+    if (tap >= 2 && tap <= 8) w2 = ws[8 + tap - 2][g];
+    if (tap >= 3 && tap <= 7) w1 = ws[3 + tap - 3][g];
+    if (tap >= 4 && tap <= 6) w0 = ws[tap - 4][g];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!kMasked || ((mask[q] >> tap) & 1u)) {
+        const float4 xi = rows[(tap + q) & 3];
+        acc[q][3] += w3.x * xi.x + w3.y * xi.y + w3.z * xi.z + w3.w * xi.w;
+        if (tap >= 2 && tap <= 8) acc[q][2] += w2.x * xi.x + w2.y * xi.y + w2.z * xi.z + w2.w * xi.w;
+        if (tap >= 3 && tap <= 7) acc[q][1] += w1.x * xi.x + w1.y * xi.y + w1.z * xi.z + w1.w * xi.w;
+        if (tap >= 4 && tap <= 6) acc[q][0] += w0.x * xi.x + w0.y * xi.y + w0.z * xi.z + w0.w * xi.w;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 temporal_conv_kernel(const float* __restrict__ x, const int* __restrict__ tok_pos, const int* __restrict__ tok_len,
                      const float* __restrict__ w /*[4][11][256]*/, const float* __restrict__ bias /*[256]*/,
                      float* __restrict__ y, int n_tokens) {
-  // One CTA walks kTok consecutive packed tokens; thread = output channel. The 11-tap input window of the thread's
-  // 4 input channels slides through registers: one new float4 per token instead of 11.
-  constexpr int kTok = 32;
-  const int o = threadIdx.x;
-  const int t0 = blockIdx.x * kTok;
-  float wr[4][11];
+  // ws[bt][g]: bt = 0..2 branch 0 (k=3, centred taps 4..6), 3..7 branch 1 (k=5, taps 3..7), 8..14 branch 2 (k=7,
+  // taps 2..8), 15..25 branch 3 (k=11, taps 0..10)
+  __shared__ float4 ws[26][64];
+  for (int idx = threadIdx.x; idx < 26 * 64; idx += 256) {
+    const int bt = idx >> 6, gg = idx & 63;
+    const int j = bt < 3 ? 0 : bt < 8 ? 1 : bt < 15 ? 2 : 3;
+    const int tap = j == 0 ? bt + 4 : j == 1 ? bt : j == 2 ? bt - 6 : bt - 15;  // index into the centred 11-tap window
+    const int o = j * 64 + gg;
+    ws[bt][gg] = make_float4(__ldg(w + (0 * 11 + tap) * kDim + o), __ldg(w + (1 * 11 + tap) * kDim + o),
+                             __ldg(w + (2 * 11 + tap) * kDim + o), __ldg(w + (3 * 11 + tap) * kDim + o));
+  }
+  __syncthreads();
+  const int g = threadIdx.x & 63;
+  const int t0 = (blockIdx.x * 4 + (threadIdx.x >> 6)) * kTcTok;
+  const int t_end = min(t0 + kTcTok, n_tokens);
+  const float b[4] = {__ldg(bias + g), __ldg(bias + 64 + g), __ldg(bias + 128 + g), __ldg(bias + 192 + g)};
+  for (int t = t0; t < t_end; t += 4) {
+    // valid taps of token t+q: 0 <= pos + tap - 5 < len; tokens past the end get an empty mask
+    unsigned mask[4];
+    bool all = true;
 #pragma unroll
-  for (int ci = 0; ci < 4; ++ci)
+    for (int q = 0; q < 4; ++q) {
+      mask[q] = 0;
+      if (t + q < t_end) {
+        const int pos = __ldg(tok_pos + t + q), len = __ldg(tok_len + t + q);
+        const int lo = max(0, 5 - pos), hi = min(10, len + 4 - pos);
+        mask[q] = hi >= lo ? ((2u << hi) - 1u) & ~((1u << lo) - 1u) : 0u;
+      }
+      all = all && mask[q] == 0x7FFu;
+    }
+    float acc[4][4];
 #pragma unroll
-    for (int tap = 0; tap < 11; ++tap) wr[ci][tap] = __ldg(w + (ci * 11 + tap) * kDim + o);
-  const float b = __ldg(bias + o);
-  const int cin = 4 * (o & 63);
-  // win[i] = x[t + i - 5] (rows of neighbouring clips included; validity is decided per tap from (pos, len)).
-  // The row entering the window is fetched one iteration ahead so its latency overlaps the FMAs.
-  auto load_row = [&](int t) -> float4 {
-    return (t >= 0 && t < n_tokens) ? *reinterpret_cast<const float4*>(x + (size_t)t * kDim + cin) : make_float4(0.f, 0.f, 0.f, 0.f);
-  };
-  float4 win[11];
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-  for (int i = 0; i < 11; ++i) win[i] = load_row(t0 + i - 5);
-  const int t_end = min(t0 + kTok, n_tokens);
-  for (int t = t0; t < t_end; ++t) {
-    const float4 incoming = load_row(t + 6);
-    const float self = x[(size_t)t * kDim + o];
-    const int pos = tok_pos[t], len = tok_len[t];
-    float acc = b;
+      for (int j = 0; j < 4; ++j) acc[q][j] = b[j];
+    if (all) temporal_conv_quad<false>(x, ws, g, t, n_tokens, mask, acc);   // warp-uniform: a warp shares its stream
+    else temporal_conv_quad<true>(x, ws, g, t, n_tokens, mask, acc);
 #pragma unroll
-    for (int tap = 0; tap < 11; ++tap) {
-      const int p = pos + tap - 5;
-      if (p >= 0 && p < len) {  // zero padding at the clip ends (Conv1d padding=k//2 on a B=1 clip)
-        const float4 xi = win[tap];
-        acc += wr[0][tap] * xi.x + wr[1][tap] * xi.y + wr[2][tap] * xi.z + wr[3][tap] * xi.w;
+    for (int q = 0; q < 4; ++q) {
+      if (t + q < t_end) {
+        const float* xs = x + (size_t)(t + q) * kDim + g;
+        float* ys = y + (size_t)(t + q) * kDim + g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ys[64 * j] = xs[64 * j] + fmaxf(acc[q][j], 0.0f);
       }
     }
-    y[(size_t)t * kDim + o] = self + fmaxf(acc, 0.0f);
-#pragma unroll
-    for (int i = 0; i < 10; ++i) win[i] = win[i + 1];
-    win[10] = incoming;
   }
 }
 

@@ -46,12 +46,12 @@ constexpr float kBnEps = 1e-5f;
 // ---------------------------------------------------------------------------------------------
 enum Stage : int {
   kStConv1 = 0, kStConv2, kStConv3, kStConv4, kStTokEmbed, kStTemporalConv, kStLayerNorm, kStQkv, kStAttention,
-  kStOutProj, kStMlp1, kStMlp2, kStPoolGemm, kStPool, kStFinal, kStMisc, kNumStages
+  kStOutProj, kStMlp1, kStMlp2, kStPoolGemm, kStPool, kStFinal, kStMisc, kStStemFused, kNumStages
 };
 const char* const kStageNames[kNumStages] = {"conv1_stem", "conv2_igemm", "conv3_igemm", "conv4_igemm_pool", "token_embed_gemm",
                                              "temporal_conv", "layernorm", "qkv_gemm", "attention", "out_proj_gemm",
                                              "mlp1_gemm_gelu", "mlp2_gemm", "pool_logits_gemm", "temporal_pool",
-                                             "final_projection", "misc"};
+                                             "final_projection", "misc", "stem_fused"};
 struct Profiler {
   bool enabled = false;
   std::vector<cudaEvent_t> pool;
@@ -443,8 +443,9 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
     // fused stem kernel (stem_fused_kernel.cuh), five K blocks of 64 = [half 0: 32 ch | half 1: 32 ch], per block and
     // half the (kh, kw) tap it holds (-1 = zero):
     //   blk0 G_A (AL0, dh=0):  (1,1) | (2,1)      blk1 G_B (AL1, dh=0): (2,2) | (1,2)      blk2 G_C (AL1, dh=0, shifted): (2,0) | (1,0)
-    //   blk3 G_D | G_E (dh=-1): (0,1) | (0,2)     blk4 G_F (dh=-1, shifted): (0,0) | zero
-    const int fused_tap[5][2][2] = {{{1, 1}, {2, 1}}, {{2, 2}, {1, 2}}, {{2, 0}, {1, 0}}, {{0, 1}, {0, 2}}, {{0, 0}, {-1, -1}}};
+    //   blk3 G_E | G_D (dh=-1): (0,2) | (0,1)     blk4 G_F (dh=-1, shifted): (0,0) | zero
+    // (blk1;blk2 and blk3;blk4 are adjacent in shared memory: each pair is the stacked 128-row operand of one N=128 UMMA)
+    const int fused_tap[5][2][2] = {{{1, 1}, {2, 1}}, {{2, 2}, {1, 2}}, {{2, 0}, {1, 0}}, {{0, 2}, {0, 1}}, {{0, 0}, {-1, -1}}};
     std::vector<float> wfu((size_t)64 * 320, 0.0f);
     for (int co = 0; co < 64; ++co)
       for (int kb = 0; kb < 5; ++kb)
@@ -616,7 +617,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     g_prof.launches += 1;
     const int grid = (int)std::min<int64_t>(F, device_sm_count());
     stem_fused_kernel<<<grid, kStemThreads, StemSmem::kTotal, st>>>(sp);
-    g_prof.mark(kStConv2, st);  // the fused kernel is accounted under conv2; conv1 shows 0
+    g_prof.mark(kStStemFused, st);
   }
   for (int64_t s0 = 0; s0 < F && !fused; s0 += g_stem_pass_frames) {
     const int64_t n = std::min<int64_t>(g_stem_pass_frames, F - s0);
@@ -753,7 +754,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   }
   // ---- multi-scale temporal convolutions (residual) ----
   {
-    const unsigned grid = (unsigned)((F + 31) / 32);
+    const unsigned grid = (unsigned)((F + 4 * kTcTok - 1) / (4 * kTcTok));
     temporal_conv_kernel<<<grid, 256, 0, st>>>(xa, tok_pos, tok_len, w->tc_w[0], w->tc_b[0], xb, (int)F);
     temporal_conv_kernel<<<grid, 256, 0, st>>>(xb, tok_pos, tok_len, w->tc_w[1], w->tc_b[1], xa, (int)F);
     g_prof.mark(kStTemporalConv, st);
@@ -785,9 +786,14 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     VFP_CUDA(cudaMemcpyAsync(features_out + (size_t)f0 * kDim, xa, (size_t)F * kDim * 4, cudaMemcpyDeviceToDevice, st));
   // ---- pooling + head ----
   {
-    EpiBiasAct::Params ep{};
-    ep.bias = w->bpool; ep.act = 1; ep.out_f32 = logits; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
-    if (token_gemm(xbf, F, kDim, w->tm_pool, kDim, ep)) return 1;
+    // fp32 logits through the TMA store path (row-per-thread fp32 stores touch 32 lines per instruction)
+    CUtensorMap tma;
+    if (make_tmap_rows_bf16(&tma, xbf, (uint64_t)F, kDim, kDim, 128, 64)) return fail("tensor map encode failed (pool in)");
+    EpiBiasActTma<false>::Params ep{};
+    if (make_tmap_out(&ep.tmap_out, logits, (uint64_t)F, kDim, false)) return fail("tensor map encode failed (pool logits)");
+    ep.bias = w->bpool; ep.N = kDim; ep.act = 1;
+    GemmShape s = plain_shape(F, kDim, kDim, 256, 64, 32);
+    VFP_CUDA((launch_gemm<256, 64, 3, EpiBiasActTma<false>>(tma, w->tm_pool, s, ep, st)));
     g_prof.mark(kStPoolGemm, st);
   }
   temporal_pool_kernel<<<(unsigned)C, 256, 0, st>>>(xa, logits, d_cu, pooled, pooled_bf);
