@@ -225,6 +225,11 @@ def run_ours(args):
         lib.vfp_set_tuning(0, args.stem_pass)
     if args.two_kernel_stem:
         lib.vfp_set_tuning(1, 0)
+    if args.stem_mode >= 0:
+        lib.vfp_set_tuning(1, args.stem_mode)
+    for kv in args.tuning:
+        k, v = kv.split("=")
+        lib.vfp_set_tuning(int(k), int(v))
     if args.conv_pass:
         lib.vfp_set_tuning(3, args.conv_pass)
     peaks = load_peaks()
@@ -331,12 +336,27 @@ def run_ours(args):
         del dbuf, host
 
     # ---- similarity join (second half of the BASELINE metric) ----
+    # N = 1: one GPU joins n x n. N > 1 (BASELINE configs[3] layout): every rank owns a row block of `join_n` rows of
+    # the (N * join_n)-row matrix; the timed region holds the NCCL all-gather of the shards AND the row-block join
+    # against all columns (global pair indices through q_row0), max over ranks.
     join = None
     if not args.no_join:
-        n_join = args.join_n
-        E = make_join_data(n_join, dev)
-        row0 = 0
-        ii, jj, ss = vfp.threshold_join_device(E, 0.95)  # warm-up + sizes
+        n_local = args.join_n
+        n_total = n_local * world
+        E_local = make_join_data(n_local, dev, seed=11 + rank)
+        if world > 1:
+            import torch.distributed as dist
+
+            E_full = torch.empty((n_total, 256), dtype=torch.float32, device=dev)
+
+            def join_step(capacity=None):
+                dist.all_gather_into_tensor(E_full, E_local)
+                return vfp.threshold_join_device(E_full, 0.95, q=E_local, q_row0=rank * n_local, capacity=capacity)
+        else:
+            def join_step(capacity=None):
+                return vfp.threshold_join_device(E_local, 0.95, capacity=capacity)
+
+        ii, jj, ss = join_step()  # warm-up + sizes
         cap = int(ii.numel()) + 4096
         torch.cuda.synchronize()
         barrier(world)
@@ -344,18 +364,24 @@ def run_ours(args):
         j0.record()
         reps = 3
         for _ in range(reps):
-            ii, jj, ss = vfp.threshold_join_device(E, 0.95, capacity=cap)
+            ii, jj, ss = join_step(cap)
         j1.record()
         torch.cuda.synchronize()
         jms = max_over_ranks(j0.elapsed_time(j1) / reps, world, dev)
-        gpairs = world * (n_join * n_join) / (jms / 1000.0) / 1e9
+        pairs_found = int(max_over_ranks(float(ii.numel()), world, dev)) if world == 1 else None
+        if world > 1:
+            t = torch.tensor([float(ii.numel())], dtype=torch.float64, device=dev)
+            dist.all_reduce(t)
+            pairs_found = int(t.item())
+        gpairs = (n_total * n_total) / (jms / 1000.0) / 1e9
         tfl = gpairs * 512 / 1000.0 / world
         join = {
-            "value": gpairs, "unit": "Gpairs/s", "n": n_join, "threshold": 0.95, "pairs_found": int(ii.numel()), "ms": jms,
-            "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tc_burst"], "unit": "TFLOP/s", "frac": tfl / peaks["tc_burst"], "traffic": None},
-            "note": "each rank joins its own N x N (replicas); the sharded all-gather join is exercised by tests/test_sharding.py",
+            "value": gpairs, "unit": "Gpairs/s", "n": n_total, "rows_per_gpu": n_local, "threshold": 0.95, "pairs_found": pairs_found, "ms": jms,
+            "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tc_burst"], "unit": "TFLOP/s per GPU", "frac": tfl / peaks["tc_burst"], "traffic": None},
+            "note": ("one GPU joins n x n" if world == 1 else
+                     f"row-block sharded: NCCL all-gather of {world} x ({n_local}, 256) fp32 shards + each rank joins its {n_local} rows against all {n_total} columns, both inside the timed region"),
         }
-        del E
+        del E_local
 
     if rank != 0:
         return
@@ -416,6 +442,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--stem-pass", type=int, default=0, help="experiment: frames per conv1+conv2 stem pass")
     ap.add_argument("--two-kernel-stem", action="store_true", help="experiment: stand-alone conv1 + conv2 kernels instead of the fused stem")
+    ap.add_argument("--stem-mode", type=int, default=-1, help="experiment: 0 two kernels, 1 fused stem with mma.sync conv1, 2 fused stem with TS-mode tcgen05 conv1")
+    ap.add_argument("--tuning", action="append", default=[], help="experiment: key=value passed to vfp_set_tuning")
     ap.add_argument("--conv-pass", type=int, default=0, help="experiment: frames per conv pass (<= 16384)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-join", action="store_true")

@@ -88,16 +88,33 @@ __device__ int g_vfp_hang_mode = 0;
 __device__ unsigned int g_vfp_hang_count = 0;
 __device__ unsigned int g_vfp_hang_log[64 * 4];
 
-// Wait used by whole warps (epilogue / producer / loader roles): polling in a tight loop costs issue slots that the
-// working warps of the same SM need (ncu on the fused stem kernel: ~60 % of all executed instructions were these
-// loops), so back off with nanosleep between polls. The single-lane TMA / UMMA roles keep the tight mbar_wait.
+// try_wait with an explicit suspend-time hint: the hardware parks the thread until the phase completes or `ns` nanoseconds
+// have passed, whichever comes first, so a waiting warp neither burns issue slots nor adds polling latency to the hand-off.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+
+// Wait used by whole warps (epilogue / producer / loader roles) and by the single-lane issuers of the stem kernels.
+// History: a tight try_wait loop cost ~60 % of all executed instructions of the fused stem kernel (the default suspend
+// time is short); backing off with __nanosleep fixed that but put up to 128 ns of polling latency on EVERY hand-off,
+// which made the stem kernels latency-bound (2.5 us per frame with all work knocked out, scripts/dev_knockout.py).
+// The suspend-time hint gives both: no spinning, wake-up when the phase completes.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(spins < 16 ? 32 : 128);
-    if ((++spins & 0x3FFF) == 0) {
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {   // <= 20 us per attempt
+    if ((++spins & 0x3FF) == 0) {
       if (t0 == 0) t0 = clock64();
       else {
         const int mode = *reinterpret_cast<volatile int*>(&g_vfp_hang_mode);

@@ -89,9 +89,78 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
+}
 // u8 -> value/255 as bf16 pairs
 __device__ __forceinline__ uint32_t u8x2_to_bf16x2(uint32_t lo, uint32_t hi) {
   return pack_bf16x2((float)lo * (1.0f / 255.0f), (float)hi * (1.0f / 255.0f));
+}
+
+// Transposer work of one frame: raw planes (three ring slots pl[0..2]; for decoder-layout u8 just three 4 KB chunks of the
+// byte stream) -> zero-haloed HWC bf16 tile. Called by `n_threads` threads with ltid = 0 .. n_threads-1.
+__device__ __forceinline__ void stem_transpose_frame(const uint8_t* const (&pl)[3], uint8_t* tile, int frame_dtype, int ltid,
+                                                     int n_threads) {
+  if (frame_dtype == kFrameBF16) {
+    // item = 8 pixels of one row: 3 x 16 B in (one per plane), 48 contiguous bytes out
+    for (int i = ltid; i < 512; i += n_threads) {
+      const int h = i >> 3, w0 = (i & 7) * 8;
+      const uint4 a = *reinterpret_cast<const uint4*>(pl[0] + (h * 64 + w0) * 2);
+      const uint4 b = *reinterpret_cast<const uint4*>(pl[1] + (h * 64 + w0) * 2);
+      const uint4 c = *reinterpret_cast<const uint4*>(pl[2] + (h * 64 + w0) * 2);
+      uint4* dst = reinterpret_cast<uint4*>(tile + (h + 2) * (kStemTilePitch * 6) + (w0 + 8) * 6);
+      // words of the HWC stream: (a0 b0)(c0 a1)(b1 c1) (a2 b2)(c2 a3)(b3 c3) ...
+      uint4 o0, o1, o2;
+      o0.x = __byte_perm(a.x, b.x, 0x5410); o0.y = __byte_perm(c.x, a.x, 0x7610); o0.z = __byte_perm(b.x, c.x, 0x7632);
+      o0.w = __byte_perm(a.y, b.y, 0x5410); o1.x = __byte_perm(c.y, a.y, 0x7610); o1.y = __byte_perm(b.y, c.y, 0x7632);
+      o1.z = __byte_perm(a.z, b.z, 0x5410); o1.w = __byte_perm(c.z, a.z, 0x7610); o2.x = __byte_perm(b.z, c.z, 0x7632);
+      o2.y = __byte_perm(a.w, b.w, 0x5410); o2.z = __byte_perm(c.w, a.w, 0x7610); o2.w = __byte_perm(b.w, c.w, 0x7632);
+      dst[0] = o0; dst[1] = o1; dst[2] = o2;
+    }
+  } else if (frame_dtype == kFrameU8) {
+    for (int i = ltid; i < 512; i += n_threads) {
+      const int h = i >> 3, w0 = (i & 7) * 8;
+      const uint2 a = *reinterpret_cast<const uint2*>(pl[0] + h * 64 + w0);
+      const uint2 b = *reinterpret_cast<const uint2*>(pl[1] + h * 64 + w0);
+      const uint2 c = *reinterpret_cast<const uint2*>(pl[2] + h * 64 + w0);
+      uint4* dst = reinterpret_cast<uint4*>(tile + (h + 2) * (kStemTilePitch * 6) + (w0 + 8) * 6);
+      uint32_t o[12];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const uint32_t av = half ? a.y : a.x, bv = half ? b.y : b.x, cv = half ? c.y : c.x;
+#pragma unroll
+        for (int pp = 0; pp < 2; ++pp) {  // pixel pair (2pp, 2pp+1) of this half
+          const uint32_t a0 = (av >> (16 * pp)) & 0xFF, a1 = (av >> (16 * pp + 8)) & 0xFF;
+          const uint32_t b0 = (bv >> (16 * pp)) & 0xFF, b1 = (bv >> (16 * pp + 8)) & 0xFF;
+          const uint32_t c0 = (cv >> (16 * pp)) & 0xFF, c1 = (cv >> (16 * pp + 8)) & 0xFF;
+          o[half * 6 + pp * 3 + 0] = u8x2_to_bf16x2(a0, b0);
+          o[half * 6 + pp * 3 + 1] = u8x2_to_bf16x2(c0, a1);
+          o[half * 6 + pp * 3 + 2] = u8x2_to_bf16x2(b1, c1);
+        }
+      }
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+      dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+    }
+  } else {
+    // decoder layout (H, W, 3) u8: the byte stream is already HWC; item = 16 bytes -> 32 bytes out
+    for (int i = ltid; i < 768; i += n_threads) {
+      const int byte0 = i * 16;
+      const int chunk = byte0 >> 12;
+      const uint4 q = *reinterpret_cast<const uint4*>((chunk == 0 ? pl[0] : chunk == 1 ? pl[1] : pl[2]) + (byte0 & 4095));
+      const int h = byte0 / 192, off = byte0 - h * 192;
+      uint4* dst = reinterpret_cast<uint4*>(tile + (h + 2) * (kStemTilePitch * 6) + 48 + 2 * off);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[2 * j] = u8x2_to_bf16x2(w[j] & 0xFF, (w[j] >> 8) & 0xFF);
+        o[2 * j + 1] = u8x2_to_bf16x2((w[j] >> 16) & 0xFF, w[j] >> 24);
+      }
+      dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+      dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __grid_constant__ StemParams p) {
@@ -168,6 +237,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
         uint32_t ph = 0;
         for (long long li = 0; li < n_local; ++li) {
           const uint8_t* src = base + (size_t)(blockIdx.x + li * gridDim.x) * (3 * plane_bytes);
+          if (li + 2 < n_local) bulk_prefetch_l2(base + (size_t)(blockIdx.x + (li + 2) * gridDim.x) * (3 * plane_bytes), 3 * plane_bytes);
           for (int c = 0; c < 3; ++c) {
             mbar_wait_relaxed(&raw_empty[slot], ph ^ 1);
             mbar_arrive_expect_tx(&raw_full[slot], plane_bytes);
@@ -234,66 +304,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_fused_kernel(const __gri
           mbar_wait_relaxed(&raw_full[s], (n / kStemRawSlots) & 1u);
           pl[c] = rawbuf + s * kStemRawSlotBytes;
         }
-        if (is_bf16) {
-          // item = 8 pixels of one row: 3 x 16 B in (one per plane), 48 contiguous bytes out
-          for (int i = ltid; i < 512; i += kXThreads) {
-            const int h = i >> 3, w0 = (i & 7) * 8;
-            const uint4 a = *reinterpret_cast<const uint4*>(pl[0] + (h * 64 + w0) * 2);
-            const uint4 b = *reinterpret_cast<const uint4*>(pl[1] + (h * 64 + w0) * 2);
-            const uint4 c = *reinterpret_cast<const uint4*>(pl[2] + (h * 64 + w0) * 2);
-            uint4* dst = reinterpret_cast<uint4*>(tile + (h + 2) * (kStemTilePitch * 6) + (w0 + 8) * 6);
-            // words of the HWC stream: (a0 b0)(c0 a1)(b1 c1) (a2 b2)(c2 a3)(b3 c3) ...
-            uint4 o0, o1, o2;
-            o0.x = __byte_perm(a.x, b.x, 0x5410); o0.y = __byte_perm(c.x, a.x, 0x7610); o0.z = __byte_perm(b.x, c.x, 0x7632);
-            o0.w = __byte_perm(a.y, b.y, 0x5410); o1.x = __byte_perm(c.y, a.y, 0x7610); o1.y = __byte_perm(b.y, c.y, 0x7632);
-            o1.z = __byte_perm(a.z, b.z, 0x5410); o1.w = __byte_perm(c.z, a.z, 0x7610); o2.x = __byte_perm(b.z, c.z, 0x7632);
-            o2.y = __byte_perm(a.w, b.w, 0x5410); o2.z = __byte_perm(c.w, a.w, 0x7610); o2.w = __byte_perm(b.w, c.w, 0x7632);
-            dst[0] = o0; dst[1] = o1; dst[2] = o2;
-          }
-        } else if (p.frame_dtype == kFrameU8) {
-          for (int i = ltid; i < 512; i += kXThreads) {
-            const int h = i >> 3, w0 = (i & 7) * 8;
-            const uint2 a = *reinterpret_cast<const uint2*>(pl[0] + h * 64 + w0);
-            const uint2 b = *reinterpret_cast<const uint2*>(pl[1] + h * 64 + w0);
-            const uint2 c = *reinterpret_cast<const uint2*>(pl[2] + h * 64 + w0);
-            uint4* dst = reinterpret_cast<uint4*>(tile + (h + 2) * (kStemTilePitch * 6) + (w0 + 8) * 6);
-            uint32_t o[12];
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              const uint32_t av = half ? a.y : a.x, bv = half ? b.y : b.x, cv = half ? c.y : c.x;
-#pragma unroll
-              for (int pp = 0; pp < 2; ++pp) {  // pixel pair (2pp, 2pp+1) of this half
-                const uint32_t a0 = (av >> (16 * pp)) & 0xFF, a1 = (av >> (16 * pp + 8)) & 0xFF;
-                const uint32_t b0 = (bv >> (16 * pp)) & 0xFF, b1 = (bv >> (16 * pp + 8)) & 0xFF;
-                const uint32_t c0 = (cv >> (16 * pp)) & 0xFF, c1 = (cv >> (16 * pp + 8)) & 0xFF;
-                o[half * 6 + pp * 3 + 0] = u8x2_to_bf16x2(a0, b0);
-                o[half * 6 + pp * 3 + 1] = u8x2_to_bf16x2(c0, a1);
-                o[half * 6 + pp * 3 + 2] = u8x2_to_bf16x2(b1, c1);
-              }
-            }
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-          }
-        } else {
-          // decoder layout (H, W, 3) u8: the byte stream is already HWC; item = 16 bytes -> 32 bytes out
-          for (int i = ltid; i < 768; i += kXThreads) {
-            const int byte0 = i * 16;
-            const int chunk = byte0 >> 12;
-            const uint4 q = *reinterpret_cast<const uint4*>((chunk == 0 ? pl[0] : chunk == 1 ? pl[1] : pl[2]) + (byte0 & 4095));
-            const int h = byte0 / 192, off = byte0 - h * 192;
-            uint4* dst = reinterpret_cast<uint4*>(tile + (h + 2) * (kStemTilePitch * 6) + 48 + 2 * off);
-            const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-            uint32_t o[8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              o[2 * j] = u8x2_to_bf16x2(w[j] & 0xFF, (w[j] >> 8) & 0xFF);
-              o[2 * j + 1] = u8x2_to_bf16x2((w[j] >> 16) & 0xFF, w[j] >> 24);
-            }
-            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-          }
-        }
+        stem_transpose_frame(pl, tile, p.frame_dtype, ltid, kXThreads);
         __syncwarp();
         if (lane == 0) {
 #pragma unroll

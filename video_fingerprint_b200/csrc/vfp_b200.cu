@@ -13,6 +13,7 @@
 #include "gemm_launch.cuh"
 #include "join_kernels.cuh"
 #include "stem_fused_kernel.cuh"
+#include "stem_ts_kernel.cuh"
 #include "token_kernels.cuh"
 #include "topk_kernels.cuh"
 
@@ -116,6 +117,8 @@ struct vfp_weights {
   CUtensorMap tm_c2, tm_c3, tm_c4;
   __nv_bfloat16* c2f_w = nullptr;  // conv2 weights in the K order of the fused stem kernel
   CUtensorMap tm_c2f;
+  __nv_bfloat16* c1ts_w = nullptr;  // conv1 weights stacked for the TS-mode stem kernel: [64 = (sw, c_out)][128 = (kh, 24 window values)]
+  CUtensorMap tm_c1ts;
   // token embedding (Linear 256->S o Linear S->256, folded) + positional table
   __nv_bfloat16* wtok = nullptr;
   float* btok = nullptr;
@@ -319,7 +322,7 @@ int vfp_device_sm_count(void) {
 
 int vfp_set_tuning(int key, long long value) {
   if (key == 0 && value >= 64) { g_stem_pass_frames = value; return 0; }
-  if (key == 1) { g_fused_stem = value != 0; return 0; }
+  if (key == 1 && value >= 0 && value <= 2) { g_fused_stem = (int)value; return 0; }
   if (key == 3 && value >= 64 && value <= kConvPassFrames) { g_conv_pass_frames = value; return 0; }
   if (key == 2) {  // hang diagnosis: timed-out mbarrier waits are logged and abandoned instead of trapping
     const int mode = value != 0;
@@ -420,6 +423,24 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
     std::vector<float> bias(32);
     for (int co = 0; co < 32; ++co) bias[co] = cb[co] * bn.scale[co] + bn.shift[co];
     if (upload(w, pack, &w->c1_wpack) || upload(w, pack_perm, &w->c1_wpack_perm) || upload(w, bias, &w->c1_bias)) return bail("");
+    // stem_ts_kernel.cuh: an A row is a horizontal pair of output pixels (sw = 0, 1) of output row oh; per filter row kh it
+    // holds 24 consecutive HWC values starting at pixel 4cx-3 channel 1: k = kh*24 + 2 + 3*p + ci is pixel 4cx-2+p, channel
+    // ci. Output pixel ow = 2cx + sw reads pixels 4cx + 2sw - 2 + kw, i.e. p = 2sw + kw. Everything else is zero.
+    std::vector<float> wts((size_t)64 * 128, 0.0f);
+    for (int sw = 0; sw < 2; ++sw)
+      for (int co = 0; co < 32; ++co)
+        for (int kh = 0; kh < 5; ++kh)
+          for (int kw = 0; kw < 5; ++kw)
+            for (int ci = 0; ci < 3; ++ci)
+              wts[(size_t)(sw * 32 + co) * 128 + kh * 24 + 2 + 3 * (2 * sw + kw) + ci] = cw[((co * 3 + ci) * 5 + kh) * 5 + kw] * bn.scale[co];
+    // K columns 120 / 121 of every A row are 1.0: the folded bias rides along as two bf16 (hi + lo)
+    for (int sw = 0; sw < 2; ++sw)
+      for (int co = 0; co < 32; ++co) {
+        const float hi = __bfloat162float(__float2bfloat16(bias[co]));
+        wts[(size_t)(sw * 32 + co) * 128 + 120] = hi;
+        wts[(size_t)(sw * 32 + co) * 128 + 121] = bias[co] - hi;
+      }
+    if (upload(w, to_bf16(wts), &w->c1ts_w)) return bail("");
   }
   // ---- conv2..4 ----
   {  // conv2: K laid out to match kConv2KBlocks (see there)
@@ -570,6 +591,7 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
   }
   if (make_tmap_rows_bf16(&w->tm_c2, w->c2_w, 64, 384, 384, 64, 64) ||
       make_tmap_rows_bf16(&w->tm_c2f, w->c2f_w, 64, 320, 320, 64, 64) ||
+      make_tmap_rows_bf16(&w->tm_c1ts, w->c1ts_w, 64, 128, 128, 64, 64) ||
       make_tmap_rows_bf16(&w->tm_c3, w->c3_w, 128, 576, 576, 128, 64) ||
       make_tmap_rows_bf16(&w->tm_c4, w->c4_w, 256, 1152, 1152, 256, 64) ||
       make_tmap_rows_bf16(&w->tm_tok, w->wtok, kDim, 256, 256, 256, 64) ||
@@ -603,7 +625,23 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
   CUtensorMap ta;
   // the fused stem streams raw frame planes with 16-byte bulk copies; fp32 frames (48 KB) do not fit its smem ring
   const bool fused = g_fused_stem && frame_dtype != VFP_FRAME_F32 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0;
-  if (fused) {
+  if (fused && g_fused_stem == 2) {
+    StemTsParams sp{};
+    sp.tmap_w2 = w->tm_c2f;
+    sp.tmap_w1 = w->tm_c1ts;
+    if (make_tmap_out(&sp.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (stem out)");
+    sp.frames = frames; sp.frame_dtype = frame_dtype; sp.n_frames = F;
+    sp.c2_bias = w->c2_b;
+    static bool configured = false;
+    if (!configured) {
+      VFP_CUDA(cudaFuncSetAttribute(stem_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemTsSmem::kTotal));
+      configured = true;
+    }
+    g_prof.launches += 1;
+    const int grid = (int)std::min<int64_t>(F, device_sm_count());
+    stem_ts_kernel<<<grid, kStemThreads, StemTsSmem::kTotal, st>>>(sp);
+    g_prof.mark(kStStemFused, st);
+  } else if (fused) {
     StemParams sp{};
     sp.tmap_w = w->tm_c2f;
     if (make_tmap_out(&sp.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (stem out)");
