@@ -77,7 +77,9 @@ def test_input_dtypes_and_batched_forward():
     for e in (e_f32, e_u8, e_bf16, e_cpu_in):
         assert cosine(e, want).min() >= COS_BAR
     assert torch.equal(e_f32, e_cpu_in)
-    assert cosine(e_f32, e_u8).min() > 0.99999
+    # two different conv-stem paths (fp32 frames: two kernels; u8 frames: fused TS-mode stem), both within COS_BAR of the
+    # oracle; against each other they differ by the summation order of bf16 products (measured 0.999989)
+    assert cosine(e_f32, e_u8).min() > 0.99998
 
 
 def test_varlen_packed_equals_per_clip_b1():
@@ -120,9 +122,10 @@ def test_return_features_and_layout_quirk():
 
 
 def test_fused_stem_matches():
-    """The fused conv1+conv2 stem kernel (default) against the two-kernel path (vfp_set_tuning(1, 0)) and the oracle, for every
-    frame format it takes (planar bf16 / planar uint8 / decoder-layout uint8; fp32 frames stay on the two-kernel path).
-    More frames than SMs so every CTA walks several frames and the ring / double buffers wrap."""
+    """Both fused conv1+conv2 stem kernels - mode 2 (default): conv1 as a TS-mode tcgen05 UMMA with its im2col rows in tensor
+    memory; mode 1: conv1 on mma.sync - against the two-kernel path (vfp_set_tuning(1, 0)) and the oracle, for every frame
+    format they take (planar bf16 / planar uint8 / decoder-layout uint8; fp32 frames stay on the two-kernel path).
+    More frames than SMs so every CTA walks several frames and the rings / double buffers wrap."""
     lib = _native.load()
     sd = make_state_dict(2, "stress")
     m = model_for(2, "stress")
@@ -134,15 +137,17 @@ def test_fused_stem_matches():
     inputs = {"bf16": x.to(torch.bfloat16), "u8": u8, "u8_hwc": u8.permute(0, 2, 3, 1).contiguous()}
     for name, frames in inputs.items():
         frames = frames.cuda()
-        fused = m.fingerprint_packed(frames, lengths).cpu()      # default path
         try:
             lib.vfp_set_tuning(1, 0)
             ref = m.fingerprint_packed(frames, lengths).cpu()
+            for mode in (1, 2):
+                lib.vfp_set_tuning(1, mode)
+                fused = m.fingerprint_packed(frames, lengths).cpu()
+                assert lib.vfp_device_error_word() == 0, (name, mode)
+                assert cosine(fused, want).min() >= COS_BAR, (name, mode)     # same bar as the default path
+                assert cosine(fused, ref).min() > 0.99995, (name, mode)       # same bf16 operands, different summation order
         finally:
-            lib.vfp_set_tuning(1, 1)
-        assert lib.vfp_device_error_word() == 0, name
-        assert cosine(fused, want).min() >= COS_BAR, name     # same bar as the default path
-        assert cosine(fused, ref).min() > 0.99995, name        # same bf16 conv1 output, different summation order
+            lib.vfp_set_tuning(1, 2)
 
 
 def test_non_default_architecture():

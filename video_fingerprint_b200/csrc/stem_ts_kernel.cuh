@@ -21,7 +21,7 @@
 // What bounds this kernel is the serial instruction stream of each role, not a pipe (scripts/dev_knockout.py, and
 // tests/cuda/microbench_handoff.cu: an mbarrier hand-off costs 100-250 cycles): with every load, store and UMMA removed
 // the barrier skeleton of the first version still took 2 us per frame. Hence two UMMA issuer warps (a unit's conv2 must not
-// wait behind the next tiles' conv1 hand-offs and vice versa), descriptors built once, a triple-buffered A operand, and
+// wait behind the next tiles' conv1 hand-offs and vice versa), descriptors built once, every TMEM buffer double buffered (conv2's two unshifted accumulators merged to make room), and
 // no per-element work that the tensor core can do instead (the bias).
 //
 // One CTA per SM, persistent over frames, 24 warps:
@@ -33,7 +33,8 @@
 //   WG3   warps 12-15   conv1 generators: HWC tile -> registers -> TMEM A operand
 //   WG4   warps 16-19   conv1 epilogue: TMEM D -> ReLU, bf16 -> conv2's A buffers (16-byte conflict-free stores)
 //   WG5   warps 20-23   transposers
-// TMEM (512 columns): conv2 accumulators 0-191 (single buffered), conv1 A 3 x 64, conv1 D 2 x 64.
+// TMEM (512 columns), everything double buffered: conv2 accumulators 2 x 128 (columns 0-63: all unshifted taps, kw = 1 and
+// kw = 2, summed by the tensor core; 64-127: the kw = 0 taps the epilogue shifts by one cell), conv1 A 2 x 64, conv1 D 2 x 64.
 #pragma once
 #include "stem_fused_kernel.cuh"
 
@@ -43,10 +44,11 @@ constexpr int kTsGenWarp0 = 12, kTsGenWarps = 4;
 constexpr int kTsEpiWarp0 = 16, kTsEpiWarps = 4;
 constexpr int kTsRawSlots = 3;
 constexpr int kTsXposeWarp1 = 20, kTsXposeWarps = 5;         // warp 2 + WG5
-constexpr int kTsABufs = 3;                                  // conv1 A operand: triple buffered (hand-off latency > one tile of UMMAs)
-constexpr int kTsColAcc = 0, kTsColA = 192, kTsColD = 384;  // TMEM column map: acc 192 | A 3 x 64 | D 2 x 64
+constexpr int kTsABufs = 2;
+constexpr int kTsColAcc = 0, kTsColA = 256, kTsColD = 384;  // TMEM column map: conv2 acc 2 x 128 | conv1 A 2 x 64 | conv1 D 2 x 64
 // development knock-out mask (compile time, -DVFP_STEM_KNOCKOUT=mask): 1 no output store, 2 no transposition, 4 no frame
-// copies, 8 no conv2 UMMAs, 16 no conv1 UMMAs, 32 no conv1-epilogue stores, 64 no generator loads
+// copies, 8 no conv2 UMMAs, 16 no conv1 UMMAs, 32 no conv1-epilogue stores, 64 no generator loads, 128 no conv2-epilogue
+// work, 256 no conv1-epilogue TMEM loads, 512 no generator TMEM stores (1023 = the bare barrier skeleton)
 #ifndef VFP_STEM_KNOCKOUT
 #define VFP_STEM_KNOCKOUT 0
 #endif
@@ -136,17 +138,17 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
   uint64_t* w_full = bars;            // [1]
   uint64_t* c1_full = bars + 1;       // [2] conv1 epilogue -> conv2 issuer (unit buffer written)
   uint64_t* c1_empty = bars + 3;      // [2] conv2 issuer -> conv1 epilogue (conv2 of the unit has read the buffer)
-  uint64_t* acc_full = bars + 5;      // [1] conv2 issuer -> conv2 epilogue
-  uint64_t* acc_empty = bars + 6;     // [1] conv2 epilogue -> conv2 issuer
+  uint64_t* acc_full = bars + 28;     // [2] conv2 issuer -> conv2 epilogue
+  uint64_t* acc_empty = bars + 30;    // [2] conv2 epilogue -> conv2 issuer
   uint64_t* tile_full = bars + 7;     // [2] transposers -> generators
   uint64_t* tile_empty = bars + 9;    // [2] generators -> transposers
   uint64_t* a_full = bars + 11;       // [3] generators -> conv1 issuer
   uint64_t* a_empty = bars + 14;      // [3] conv1 issuer -> generators
   uint64_t* d_full = bars + 17;       // [2] conv1 issuer -> conv1 epilogue
   uint64_t* d_empty = bars + 19;      // [2] conv1 epilogue -> conv1 issuer
-  uint64_t* raw_full = bars + 21;     // [3] bulk copy -> transposers
-  uint64_t* raw_empty = bars + 24;    // [3] transposers -> bulk copy issuer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 27);
+  uint64_t* raw_full = bars + 32;     // [5] bulk copy -> transposers
+  uint64_t* raw_empty = bars + 37;    // [5] transposers -> bulk copy issuer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -163,10 +165,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
     mbar_init(w_full, 1);
     mbar_init(&c1_full[0], 2 * kTsEpiWarps);       // two tiles
     mbar_init(&c1_full[1], 2 * kTsEpiWarps + 1);   // + the halo cell row written by the warp that owns cell row 7
-    mbar_init(acc_full, 1);
-    mbar_init(acc_empty, kStemEpiWarps);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&c1_empty[i], 1);
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], kStemEpiWarps);
       mbar_init(&tile_full[i], kTsXposeWarps);
       mbar_init(&tile_empty[i], kTsGenWarps);
       mbar_init(&d_full[i], 1);
@@ -285,32 +287,34 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
       mbar_wait_relaxed(w_full, 0);
       const uint32_t w2_lo = desc_lo_sw128(smem_u32(w2buf));
       const uint32_t c1_lo = desc_lo_sw128(smem_u32(c1buf));
-      const uint32_t d_r = tmem_base + kTsColAcc, d_m = d_r + 64;
       for (int u = 0; u < n_units; ++u) {
         const int b = u & 1;
-        mbar_wait_relaxed(acc_empty, (uint32_t)((u & 1) ^ 1));
-        mbar_wait_relaxed(&c1_full[b], (uint32_t)((u >> 1) & 1));
+        const uint32_t ph = (uint32_t)((u >> 1) & 1);
+        mbar_wait_relaxed(&acc_empty[b], ph ^ 1);
+        mbar_wait_relaxed(&c1_full[b], ph);
         tc_fence_after();
         if (lane == 0) {
-          // same four groups as stem_fused_kernel (R = columns 0-63: kw = 1 taps; M = columns 64-191: kw = 2 | kw = 0).
-          // descriptor arithmetic in 16-byte units: a K step is 2, a cell row of the buffer 128, a weight block 512
+          // the four tap groups of stem_fused_kernel, but the unshifted ones share an accumulator: columns 0-63 collect the
+          // kw = 1 taps (N = 64 UMMAs on AL0) AND the kw = 2 taps (first half of the stacked N = 128 UMMAs on AL1), columns
+          // 64-127 the kw = 0 taps. Descriptor arithmetic in 16-byte units: K step 2, buffer cell row 128, weight block 512
+          const uint32_t d_acc = tmem_base + kTsColAcc + b * 128;
           const uint32_t al0 = c1_lo + b * (kStemUnitBytes >> 4), al1 = al0 + (kStemABuf >> 4);
           if (!(kTsKnock & 8)) {
-            umma_ss_lo<false>(d_r, al0 + 128, w2_lo, idesc64);                       // G_A  k = 0
-            umma_ss_lo<false>(d_m, al1 + 128, w2_lo + 512, idesc128);                // G_BC k = 0
+            umma_ss_lo<false>(d_acc, al1 + 128, w2_lo + 512, idesc128);               // G_BC k = 0 initialises all 128 columns
+            umma_ss_lo<true>(d_acc, al0 + 128, w2_lo, idesc64);                       // G_A  k = 0
 #pragma unroll
             for (int k = 1; k < 4; ++k) {
-              umma_ss_lo<true>(d_r, al0 + 128 + 2 * k, w2_lo + 2 * k, idesc64);            // G_A
-              umma_ss_lo<true>(d_m, al1 + 128 + 2 * k, w2_lo + 512 + 2 * k, idesc128);     // G_BC
+              umma_ss_lo<true>(d_acc, al0 + 128 + 2 * k, w2_lo + 2 * k, idesc64);            // G_A
+              umma_ss_lo<true>(d_acc, al1 + 128 + 2 * k, w2_lo + 512 + 2 * k, idesc128);     // G_BC
             }
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-              umma_ss_lo<true>(d_r, al0 + 2 * (2 + k), w2_lo + 3 * 512 + 2 * (2 + k), idesc64);   // G_D
-              umma_ss_lo<true>(d_m, al1 + 2 * k, w2_lo + 3 * 512 + 2 * k, idesc128);              // G_EF
+              umma_ss_lo<true>(d_acc, al0 + 2 * (2 + k), w2_lo + 3 * 512 + 2 * (2 + k), idesc64);   // G_D
+              umma_ss_lo<true>(d_acc, al1 + 2 * k, w2_lo + 3 * 512 + 2 * k, idesc128);              // G_EF
             }
           }
           umma_commit(&c1_empty[b]);
-          umma_commit(acc_full);
+          umma_commit(&acc_full[b]);
         }
         __syncwarp();
       }
@@ -322,28 +326,43 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
     setmaxnreg_dec<56>();
     const int quarter = warp & 3;
     const int col_half = (warp - kStemEpiWarp0) >> 2;
+    const bool first_cell = (lane & 15) == 0;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kTsColAcc + col_half * 32;
+    // Output: bf16 rows staged in shared memory (swizzled, conflict-free 16-byte stores) and written by the TMA unit.
+    // (Direct 16-byte global stores from the row-per-thread layout touch 32 lines per instruction: measured 25 % slower.)
     uint8_t* dst = stagebuf + (warp - kStemEpiWarp0) * 2048;
     uint8_t* r0 = dst + lane * 64;
     const int sw = (lane >> 1) & 3;
-    const bool first_cell = (lane & 15) == 0;
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kTsColAcc + col_half * 32;
     int out_row = (int)blockIdx.x * 256 + quarter * 32;   // conv2 output row (pixel) of this warp's 32 rows, unit 0
     for (int u = 0; u < n_units; ++u) {
-      mbar_wait_relaxed(acc_full, (uint32_t)(u & 1));
+      const int b = u & 1;
+      mbar_wait_relaxed(&acc_full[b], (uint32_t)((u >> 1) & 1));
       tc_fence_after();
       if (lane == 0) tma_store_wait_read<0>();
       __syncwarp();
+      // software pipelined over the four 8-column chunks: the TMEM loads of chunk c+1 are in flight while chunk c is
+      // shuffled, summed and stored (v0: kw = 1 and kw = 2 taps, v2: kw = 0 taps of the cell to the left)
+      if (kTsKnock & 128) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);
+        continue;
+      }
+      uint32_t va[2][8], vb[2][8];
+      tmem_ld_32x8(taddr + b * 128, va[0]);
+      tmem_ld_32x8(taddr + b * 128 + 64, vb[0]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v0[8], v1[8], v2[8];
-        tmem_ld_32x8(taddr + 8 * c, v0);         // kw = 1 taps
-        tmem_ld_32x8(taddr + 64 + 8 * c, v1);    // kw = 2 taps
-        tmem_ld_32x8(taddr + 128 + 8 * c, v2);   // kw = 0 taps of the cell to the left
+        uint32_t(&v0)[8] = va[c & 1];
+        uint32_t(&v2)[8] = vb[c & 1];
         tmem_ld_wait();
-        if (c == 3) {  // everything this warp needs has left TMEM: the next unit's conv2 may overwrite it
+        if (c < 3) {
+          tmem_ld_32x8(taddr + b * 128 + 8 * (c + 1), va[(c + 1) & 1]);
+          tmem_ld_32x8(taddr + b * 128 + 64 + 8 * (c + 1), vb[(c + 1) & 1]);
+        } else {  // everything this warp needs has left TMEM
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty);
+          if (lane == 0) mbar_arrive(&acc_empty[b]);
         }
         uint32_t q[4];
 #pragma unroll
@@ -355,7 +374,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
           for (int j = 0; j < 4; ++j) {
             float s = __shfl_up_sync(0xffffffffu, __uint_as_float(v2[i + j]), 1);
             if (first_cell) s = 0.0f;
-            x[j] = __uint_as_float(v0[i + j]) + __uint_as_float(v1[i + j]) + bias4[j] + s;
+            x[j] = __uint_as_float(v0[i + j]) + bias4[j] + s;
           }
           q[i / 2] = relu_pack_bf16x2(x[0], x[1]);
           q[i / 2 + 1] = relu_pack_bf16x2(x[2], x[3]);
@@ -404,9 +423,11 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
         }
         mbar_wait_relaxed(&a_empty[ab], aph ^ 1);
         tc_fence_after();
-        tmem_st_32x32(lane_base + ab * 64, v);
-        tmem_st_32x32(lane_base + ab * 64 + 32, v + 32);
-        tmem_st_wait();
+        if (!(kTsKnock & 512)) {
+          tmem_st_32x32(lane_base + ab * 64, v);
+          tmem_st_32x32(lane_base + ab * 64 + 32, v + 32);
+          tmem_st_wait();
+        }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_full[ab]);
@@ -436,6 +457,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
       uint32_t packed[2][16];
 #pragma unroll
       for (int sw = 0; sw < 2; ++sw) {
+        if (kTsKnock & 256) break;
         uint32_t d[32];
         tmem_ld_32x32(lane_base + b * 64 + sw * 32, d);
         tmem_ld_wait();

@@ -246,7 +246,7 @@ int64_t g_stem_pass_frames = kConvPassFrames;
 // conv1+conv2 in one kernel (stem_fused_kernel.cuh: conv1's output stays in shared memory as conv2's UMMA operand).
 // Measured on B200 (10k x 64-frame clips): 18.4 ms vs 13.4 + 12.9 ms for the two HBM-bound kernels, so it is the
 // default for u8 / bf16 frames; vfp_set_tuning(1, 0) selects the two-kernel path (always used for fp32 frames).
-int g_fused_stem = 1;
+int g_fused_stem = 2;
 
 struct TokenWs {
   size_t cu, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, h, logits, xbf, pooled, pooled_bf, head_h, total;
