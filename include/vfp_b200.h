@@ -107,6 +107,26 @@ int vfp_topk_ip(const float* q, const float* db, int64_t n_q, int64_t n_db, int 
                 float screen_margin, float* out_s, int64_t* out_idx, uint64_t* flags_out, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* Evaluation metrics over an embedding set - the trainer's use of the same N x N similarity matrix
+ * (/root/reference/train.py:285-358 compute_discrimination_metrics, :439-481 _compute_retrieval_metrics), computed
+ * without storing the matrix. All scores are exact fp32 (one fmaf chain over k = 0 .. dim-1).
+ * vfp_pair_scores: out_s[t] = <e[pair_i[t]], e[pair_j[t]]> for m listed pairs (device arrays).
+ * vfp_pair_stats: one pass over every ordered pair (i, j), i != j. A "positive" of row i is a column with the same
+ * video id; the caller lists them in CSR form (row_ptr (n+1), pos_idx (m), device) with their scores pos_score (m)
+ * from vfp_pair_scores and the same scores sorted ascending (sorted_intra (m)). Outputs (device):
+ *   rank_greater[q]    = #{j != i : s_ij >  pos_score[q]}             (-> rank of the positive, R@k, mAP)
+ *   rank_tie_before[q] = #{j != i, j < pos_idx[q] : s_ij == pos_score[q]}
+ *   sums[4]   = sum / sum of squares of the intra-video scores, then of the inter-video scores (double)
+ *   counts[20] = n_intra, n_inter, sum over inter scores s of #{intra <= s}, of #{intra < s} (-> AUC-ROC in its
+ *                Mann-Whitney form), then for each of the <= 8 thresholds #{intra >= thr} (8 slots) and #{inter >= thr}.
+ * `thresholds` is a HOST array of n_thresholds floats. dim must be a multiple of 16, e 16-byte aligned. */
+int vfp_pair_scores(const float* e, int64_t n, int dim, const int32_t* pair_i, const int32_t* pair_j, int64_t m,
+                    float* out_s, void* stream);
+int vfp_pair_stats(const float* e, const int32_t* video_ids, int64_t n, int dim, const int32_t* row_ptr,
+                   const int32_t* pos_idx, const float* pos_score, const float* sorted_intra, int64_t m,
+                   const float* thresholds, int n_thresholds, uint32_t* rank_greater, uint32_t* rank_tie_before,
+                   double* sums, uint64_t* counts, void* stream);
+
 /* Stage profiler (measurement hook, used by bench.py): when enabled, vfp_forward records CUDA events between
  * its stages on the caller's stream. vfp_profile_read synchronises on the last event and returns the accumulated
  * milliseconds per stage (vfp_profile_num_stages entries, names via vfp_profile_stage_name) and the number of

@@ -6,6 +6,7 @@ Public surface (mirrors /root/reference/model.py and /root/reference/fingerprint
     VideoFingerprintScanner                          find_duplicates / save_results / per-video semantics
     threshold_join, topk_inner_product               the two similarity-search primitives
     sharding                                         multi-GPU partitioning + NCCL all-gather join
+    compute_retrieval_metrics, compute_discrimination_metrics   the trainer's evaluation metrics over the same N x N scores
 
 All device work goes through libvfp_b200.so (include/vfp_b200.h); there is no CPU or PyTorch fallback.
 """
@@ -19,8 +20,11 @@ from .fingerprint import (  # noqa: F401
     topk_inner_product,
     topk_inner_product_device,
 )
+from .metrics import compute_discrimination_metrics, compute_retrieval_metrics  # noqa: F401
 
 __all__ = [
+    "compute_retrieval_metrics",
+    "compute_discrimination_metrics",
     "create_model",
     "VideoFingerprintAttention",
     "VideoFingerprintScanner",

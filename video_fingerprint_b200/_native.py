@@ -29,6 +29,8 @@ EXPORTED_SYMBOLS = (
     "vfp_join_threshold",
     "vfp_topk_workspace_bytes",
     "vfp_topk_ip",
+    "vfp_pair_scores",
+    "vfp_pair_stats",
     "vfp_device_error_word",
     "vfp_profile_enable",
     "vfp_profile_num_stages",
@@ -86,6 +88,10 @@ def load() -> C.CDLL:
     lib.vfp_topk_workspace_bytes.argtypes = [i64, i64, i32]
     lib.vfp_topk_ip.restype = i32
     lib.vfp_topk_ip.argtypes = [vp, vp, i64, i64, i32, i32, f32, vp, vp, vp, vp, sz, vp]
+    lib.vfp_pair_scores.restype = i32
+    lib.vfp_pair_scores.argtypes = [vp, i64, i32, vp, vp, i64, vp, vp]
+    lib.vfp_pair_stats.restype = i32
+    lib.vfp_pair_stats.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp]
     lib.vfp_profile_enable.restype = i32
     lib.vfp_profile_enable.argtypes = [i32]
     lib.vfp_profile_num_stages.restype = i32

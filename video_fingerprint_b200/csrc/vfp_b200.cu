@@ -12,6 +12,7 @@
 #include "conv1_kernel.cuh"
 #include "gemm_launch.cuh"
 #include "join_kernels.cuh"
+#include "metrics_kernels.cuh"
 #include "stem_fused_kernel.cuh"
 #include "stem_ts_kernel.cuh"
 #include "token_kernels.cuh"
@@ -978,6 +979,47 @@ int vfp_topk_ip(const float* q, const float* db, int64_t n_q, int64_t n_db, int 
   const int rc = topk_run(q, db, n_q, n_db, k, screen_margin, out_s, out_idx, reinterpret_cast<unsigned long long*>(flags_out),
                           static_cast<uint8_t*>(workspace), static_cast<cudaStream_t>(stream), &err);
   if (rc) return fail("vfp_topk_ip: " + err);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// evaluation metrics over an embedding set (train.py:285-358, 439-481)
+// ---------------------------------------------------------------------------------------------
+int vfp_pair_scores(const float* e, int64_t n, int dim, const int32_t* pair_i, const int32_t* pair_j, int64_t m, float* out_s,
+                    void* stream) {
+  if (!e || (m > 0 && (!pair_i || !pair_j || !out_s))) return fail("vfp_pair_scores: null argument");
+  if (n <= 0 || dim <= 0 || n > 0x7fffff00LL || m > 0x7fffff00LL) return fail("vfp_pair_scores: bad size");
+  if (m == 0) return 0;
+  pair_scores_kernel<<<(unsigned)((m + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(e, dim, pair_i, pair_j, (int)m, out_s);
+  VFP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vfp_pair_stats(const float* e, const int32_t* video_ids, int64_t n, int dim, const int32_t* row_ptr, const int32_t* pos_idx,
+                   const float* pos_score, const float* sorted_intra, int64_t m, const float* thresholds, int n_thresholds,
+                   uint32_t* rank_greater, uint32_t* rank_tie_before, double* sums, uint64_t* counts, void* stream) {
+  if (!e || !video_ids || !row_ptr || !sums || !counts) return fail("vfp_pair_stats: null argument");
+  if (m > 0 && (!pos_idx || !pos_score || !sorted_intra || !rank_greater || !rank_tie_before)) return fail("vfp_pair_stats: null argument");
+  if (n <= 0 || n > 0x7fffff00LL || m < 0 || m > 0x7fffff00LL) return fail("vfp_pair_stats: bad size");
+  if (dim <= 0 || dim % kMsK != 0) return fail("vfp_pair_stats: dim must be a multiple of 16");
+  if (n_thresholds < 0 || n_thresholds > kMsMaxThr || (n_thresholds > 0 && !thresholds)) return fail("vfp_pair_stats: at most 8 thresholds");
+  if ((reinterpret_cast<uintptr_t>(e) & 15) != 0) return fail("vfp_pair_stats: embeddings must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PairStatsParams p{};
+  p.e = e; p.ids = video_ids; p.n = (int)n; p.dim = dim; p.row_ptr = row_ptr; p.pos_idx = pos_idx; p.pos_score = pos_score;
+  p.sorted_intra = sorted_intra; p.m = (int)m; p.n_thr = n_thresholds;
+  for (int t = 0; t < n_thresholds; ++t) p.thr[t] = thresholds[t];   // HOST array
+  p.rank_greater = rank_greater; p.rank_tie_before = rank_tie_before; p.sums = sums;
+  p.counts = reinterpret_cast<unsigned long long*>(counts);
+  VFP_CUDA(cudaMemsetAsync(sums, 0, 4 * sizeof(double), st));
+  VFP_CUDA(cudaMemsetAsync(counts, 0, (4 + 2 * kMsMaxThr) * sizeof(uint64_t), st));
+  if (m > 0) {
+    VFP_CUDA(cudaMemsetAsync(rank_greater, 0, (size_t)m * 4, st));
+    VFP_CUDA(cudaMemsetAsync(rank_tie_before, 0, (size_t)m * 4, st));
+  }
+  const unsigned tiles = (unsigned)((n + kMsTile - 1) / kMsTile);
+  pair_stats_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(p);
+  VFP_CUDA(cudaGetLastError());
   return 0;
 }
 
