@@ -395,10 +395,16 @@ def run_ours(args):
     gbs = STAGE_BYTES.get(dom, 0) * n_clips / (dom_ms / 1000.0) / 1e9
     frac_t, frac_h = tflops / peaks["tc_sustained"], gbs / peaks["hbm"]
     hbm_bound = frac_h > frac_t  # the binding roofline is the one the kernel sits closer to
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r01_v5_stem_ts_full.txt:
+    # dram__bytes_read.sum + dram__bytes_write.sum of one stem launch over a 16 384-frame conv pass); below the algorithmic
+    # 939.5 MB because the tail of the output is still in L2 when the kernel ends
+    ncu_traffic = {"stem_fused": 402.772480e6 + 491.417344e6}
     roofline = {
         "bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
         "achieved": gbs if hbm_bound else tflops, "peak": peaks["hbm"] if hbm_bound else peaks["tc_sustained"],
-        "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": frac_h if hbm_bound else frac_t, "traffic": None,
+        "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": frac_h if hbm_bound else frac_t,
+        "traffic": ncu_traffic.get(dom) if (n_clips * T_FRAMES) >= 16384 else None,
+        "traffic_note": "bytes per launch (one 16 384-frame conv pass) from the committed ncu capture of this kernel; algorithmic bytes per launch = %.1f MB" % (STAGE_BYTES.get(dom, 0) / T_FRAMES * 16384 / 1e6),
         "peak_source": f"{peaks['source']} ({'HBM copy bandwidth' if hbm_bound else 'sustained bf16, kernel timed inside a long step'})",
         "other_roofline": {"tensor_tflops": tflops, "tensor_frac": frac_t, "hbm_gbs": gbs, "hbm_frac": frac_h},
         "launches_per_step": launches_per_step, "ms_per_step_in_kernel": dom_ms,

@@ -54,19 +54,30 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
-def build_selftest() -> str:
+DEVICE_TOOLS = ("selftest_gemm", "selftest_ts_mma", "microbench_tensor", "microbench_handoff", "microbench_tmem")
+
+
+def build_selftest(name: str = "selftest_gemm") -> str:
+    """Device self-tests and micro-benchmarks under tests/cuda/ (stand-alone binaries, run on a B200)."""
     out_dir = os.path.join(ROOT, "build")
     os.makedirs(out_dir, exist_ok=True)
-    out = os.path.join(out_dir, "selftest_gemm")
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", out, os.path.join(ROOT, "tests", "cuda", "selftest_gemm.cu")]
+    out = os.path.join(out_dir, name)
+    src = os.path.join(ROOT, "tests", "cuda", name + ".cu")
+    if os.path.exists(out) and os.path.getmtime(out) >= max(os.path.getmtime(src), _sources_mtime()):
+        return out
+    cmd = [_nvcc(), *NVCC_FLAGS, "-o", out, src]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     return out
 
 
+def build_tools() -> list:
+    return [build_selftest(n) for n in DEVICE_TOOLS]
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "selftest":
-        print(build_selftest())
+        print("\n".join(build_tools()))
     else:
         print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
