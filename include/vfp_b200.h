@@ -107,6 +107,16 @@ int vfp_topk_ip(const float* q, const float* db, int64_t n_q, int64_t n_db, int 
                 float screen_margin, float* out_s, int64_t* out_idx, uint64_t* flags_out, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* Frame preprocessing of the scanner (/root/reference/fingerprint.py:186-214 _preprocess_frames): cv2.resize(frame,
+ * INTER_AREA) so that the short side becomes 64 (new size truncated with int() like the reference), then the centre
+ * 64 x 64 crop. `frames_hwc`: device uint8 (n_frames, height, width, 3), all frames of one size; `out_hwc64`: device
+ * uint8 (n_frames, 64, 64, 3), which vfp_forward accepts as VFP_FRAME_U8_HWC (the /255 and the HWC->CHW permute of
+ * fingerprint.py:210-212 happen inside the stem kernel). Bit-exact with OpenCV 4.x INTER_AREA down-scaling (general,
+ * integer-factor and 2 x 2 code paths); frames with a side below 64 pixels (up-scaling) are rejected. */
+size_t vfp_preprocess_workspace_bytes(int height, int width);
+int vfp_preprocess_frames(const uint8_t* frames_hwc, int n_frames, int height, int width, uint8_t* out_hwc64,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Evaluation metrics over an embedding set - the trainer's use of the same N x N similarity matrix
  * (/root/reference/train.py:285-358 compute_discrimination_metrics, :439-481 _compute_retrieval_metrics), computed
  * without storing the matrix. All scores are exact fp32 (one fmaf chain over k = 0 .. dim-1).

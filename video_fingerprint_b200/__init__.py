@@ -15,6 +15,7 @@ from .fingerprint import (  # noqa: F401
     VideoFingerprintScanner,
     group_pairs_direct,
     group_pairs_topk,
+    preprocess_frames_device,
     threshold_join,
     threshold_join_device,
     topk_inner_product,
@@ -23,6 +24,7 @@ from .fingerprint import (  # noqa: F401
 from .metrics import compute_discrimination_metrics, compute_retrieval_metrics  # noqa: F401
 
 __all__ = [
+    "preprocess_frames_device",
     "compute_retrieval_metrics",
     "compute_discrimination_metrics",
     "create_model",

@@ -29,6 +29,8 @@ EXPORTED_SYMBOLS = (
     "vfp_join_threshold",
     "vfp_topk_workspace_bytes",
     "vfp_topk_ip",
+    "vfp_preprocess_workspace_bytes",
+    "vfp_preprocess_frames",
     "vfp_pair_scores",
     "vfp_pair_stats",
     "vfp_device_error_word",
@@ -88,6 +90,10 @@ def load() -> C.CDLL:
     lib.vfp_topk_workspace_bytes.argtypes = [i64, i64, i32]
     lib.vfp_topk_ip.restype = i32
     lib.vfp_topk_ip.argtypes = [vp, vp, i64, i64, i32, i32, f32, vp, vp, vp, vp, sz, vp]
+    lib.vfp_preprocess_workspace_bytes.restype = sz
+    lib.vfp_preprocess_workspace_bytes.argtypes = [i32, i32]
+    lib.vfp_preprocess_frames.restype = i32
+    lib.vfp_preprocess_frames.argtypes = [vp, i32, i32, i32, vp, vp, sz, vp]
     lib.vfp_pair_scores.restype = i32
     lib.vfp_pair_scores.argtypes = [vp, i64, i32, vp, vp, i64, vp, vp]
     lib.vfp_pair_stats.restype = i32

@@ -1,0 +1,68 @@
+// On-device restatement of the scanner's frame preprocessing (/root/reference/fingerprint.py:186-214 _preprocess_frames):
+// cv2.resize(frame, (new_w, new_h), INTER_AREA) so that the short side becomes 64, centre crop to 64 x 64. The uint8 result
+// (decoder layout H, W, 3) feeds the fused stem directly (frame_dtype VFP_FRAME_U8_HWC, which also does the /255).
+// Bit-exact with OpenCV 4.x for down-scaling (both scale factors >= 1), its three code paths:
+//   * general (non-integer scale): float tables of (source index, weight) per destination index (computeResizeAreaTab);
+//     per source row   buf = buf + S * alpha   over the x entries in order, then   sum = beta * buf   (first row) or
+//     sum = sum + beta * buf; saturate_cast<uchar> = round half to even. Separate fmul / fadd, exactly OpenCV's order.
+//   * integer scale factors: integer box sum, then round-half-even(float(sum) * float(1 / area));
+//   * both factors == 2: (sum + 2) >> 2.
+// One CTA per (output row, frame): every needed source row segment is staged through shared memory with coalesced loads
+// (a 1080p frame is read exactly once: 3.5 MB for the 64 x 64 crop), thread (dx, c) then walks its own table entries.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace vfp {
+
+struct PreprocessParams {
+  const uint8_t* src;    // [frames][H][W][3]
+  uint8_t* dst;          // [frames][64][64][3]
+  int H, W;
+  int mode;              // 0 general, 1 integer scale (float multiply), 2 exact 2 x 2
+  float inv_area;        // modes 1, 2
+  // tables over the CROPPED destination window (64 entries each): entry ranges and the source span they touch
+  const int* x_begin;    // [65] prefix into x_si / x_alpha
+  const int* x_si;
+  const float* x_alpha;
+  const int* y_begin;    // [65]
+  const int* y_si;
+  const float* y_beta;
+  int sx_min, sx_count;  // source columns [sx_min, sx_min + sx_count) cover every x entry
+};
+
+constexpr int kPreMaxSpan = 8192;   // bytes of one staged source row segment (sx_count * 3 <= 8192: scale factors up to ~42)
+
+__global__ void __launch_bounds__(192) preprocess_area_kernel(const PreprocessParams p) {
+  __shared__ uint8_t row[kPreMaxSpan];
+  const int dy = blockIdx.x, f = blockIdx.y;
+  const int dx = threadIdx.x / 3, c = threadIdx.x - 3 * dx;
+  const int xb = p.x_begin[dx], xe = p.x_begin[dx + 1];
+  const int yb = p.y_begin[dy], ye = p.y_begin[dy + 1];
+  const uint8_t* frame = p.src + (size_t)f * p.H * p.W * 3;
+  const int span = p.sx_count * 3;
+  float sum = 0.0f;
+  int isum = 0;
+  for (int j = yb; j < ye; ++j) {
+    const uint8_t* srow = frame + ((size_t)p.y_si[j] * p.W + p.sx_min) * 3;
+    __syncthreads();
+    for (int i = threadIdx.x; i < span; i += 192) row[i] = srow[i];
+    __syncthreads();
+    if (p.mode == 0) {
+      float buf = 0.0f;
+      for (int k = xb; k < xe; ++k) buf = __fadd_rn(buf, __fmul_rn((float)row[(p.x_si[k] - p.sx_min) * 3 + c], p.x_alpha[k]));
+      const float t = __fmul_rn(p.y_beta[j], buf);
+      sum = (j == yb) ? t : __fadd_rn(sum, t);
+    } else {
+      for (int k = xb; k < xe; ++k) isum += row[(p.x_si[k] - p.sx_min) * 3 + c];
+    }
+  }
+  float v;
+  if (p.mode == 0) v = sum;
+  else if (p.mode == 1) v = __fmul_rn((float)isum, p.inv_area);
+  else v = (float)((isum + 2) >> 2);
+  const int r = __float2int_rn(v);    // round half to even, like cvRound
+  p.dst[(((size_t)f * 64 + dy) * 64 + dx) * 3 + c] = (uint8_t)min(max(r, 0), 255);
+}
+
+}  // namespace vfp

@@ -13,6 +13,7 @@
 #include "gemm_launch.cuh"
 #include "join_kernels.cuh"
 #include "metrics_kernels.cuh"
+#include "preprocess_kernels.cuh"
 #include "stem_fused_kernel.cuh"
 #include "stem_ts_kernel.cuh"
 #include "token_kernels.cuh"
@@ -1019,6 +1020,88 @@ int vfp_pair_stats(const float* e, const int32_t* video_ids, int64_t n, int dim,
   }
   const unsigned tiles = (unsigned)((n + kMsTile - 1) / kMsTile);
   pair_stats_kernel<<<dim3(tiles, tiles), 256, 0, st>>>(p);
+  VFP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// frame preprocessing (fingerprint.py:186-214): INTER_AREA resize of the short side to 64 + centre crop
+// ---------------------------------------------------------------------------------------------
+namespace {
+// OpenCV computeResizeAreaTab (imgproc/src/resize.cpp), one destination axis, entries of destination indices [d0, d0 + 64)
+void area_table(int ssize, int dsize, double scale, int d0, std::vector<int>* begin, std::vector<int>* si, std::vector<float>* alpha) {
+  begin->assign(65, 0);
+  si->clear();
+  alpha->clear();
+  for (int d = d0; d < d0 + 64; ++d) {
+    (*begin)[d - d0] = (int)si->size();
+    const double fsx1 = d * scale, fsx2 = fsx1 + scale;
+    const double cell = std::min(scale, ssize - fsx1);
+    int sx1 = (int)ceil(fsx1), sx2 = (int)floor(fsx2);
+    sx2 = std::min(sx2, ssize - 1);
+    sx1 = std::min(sx1, sx2);
+    if (sx1 - fsx1 > 1e-3) { si->push_back(sx1 - 1); alpha->push_back((float)((sx1 - fsx1) / cell)); }
+    for (int sx = sx1; sx < sx2; ++sx) { si->push_back(sx); alpha->push_back((float)(1.0 / cell)); }
+    if (fsx2 - sx2 > 1e-3) { si->push_back(sx2); alpha->push_back((float)(std::min(std::min(fsx2 - sx2, 1.0), cell) / cell)); }
+  }
+  (*begin)[64] = (int)si->size();
+}
+}  // namespace
+
+size_t vfp_preprocess_workspace_bytes(int height, int width) {
+  // tables: two axes x (65 ints + entries * (int + float)); an axis has at most 64 * (scale + 2) entries
+  const size_t per_axis = 65 * 4 + (size_t)(64 * 2 + std::max(height, width) + 64) * 8;
+  return 2 * per_axis + 256;
+}
+
+int vfp_preprocess_frames(const uint8_t* frames_hwc, int n_frames, int height, int width, uint8_t* out_hwc64, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (!frames_hwc || !out_hwc64 || !workspace) return fail("vfp_preprocess_frames: null argument");
+  if (n_frames <= 0 || n_frames > 65535) return fail("vfp_preprocess_frames: 1 .. 65535 frames per call");
+  if (height < 64 || width < 64) return fail("vfp_preprocess_frames: frames smaller than 64 pixels are not supported (INTER_AREA would up-scale)");
+  if (workspace_bytes < vfp_preprocess_workspace_bytes(height, width)) return fail("vfp_preprocess_frames: workspace too small");
+  // fingerprint.py:190-196
+  int new_w, new_h;
+  if (height < width) { new_h = 64; new_w = (int)((double)width * 64 / height); }
+  else { new_w = 64; new_h = (int)((double)height * 64 / width); }
+  // cv::resize: inv_scale = dsize / ssize, scale = 1. / inv_scale (not ssize / dsize: the last bit can differ)
+  const double scale_x = 1.0 / ((double)new_w / width), scale_y = 1.0 / ((double)new_h / height);
+  const int start_h = (new_h - 64) / 2, start_w = (new_w - 64) / 2;   // fingerprint.py:201-202
+  const int isx = (int)lrint(scale_x), isy = (int)lrint(scale_y);
+  const bool fast = fabs(scale_x - isx) < 2.220446049250313e-16 && fabs(scale_y - isy) < 2.220446049250313e-16;
+  std::vector<int> xb, xs, yb, ys;
+  std::vector<float> xa, ya;
+  if (fast) {   // integer box: every source column / row of the box with weight 1
+    xb.resize(65); yb.resize(65);
+    for (int d = 0; d <= 64; ++d) { xb[d] = d * isx; yb[d] = d * isy; }
+    for (int d = 0; d < 64; ++d) {
+      for (int k = 0; k < isx; ++k) { xs.push_back((start_w + d) * isx + k); xa.push_back(1.0f); }
+      for (int k = 0; k < isy; ++k) { ys.push_back((start_h + d) * isy + k); ya.push_back(1.0f); }
+    }
+  } else {
+    area_table(width, new_w, scale_x, start_w, &xb, &xs, &xa);
+    area_table(height, new_h, scale_y, start_h, &yb, &ys, &ya);
+  }
+  int sx_min = xs[0], sx_max = xs[0];
+  for (int v : xs) { sx_min = std::min(sx_min, v); sx_max = std::max(sx_max, v); }
+  PreprocessParams p{};
+  p.sx_min = sx_min; p.sx_count = sx_max - sx_min + 1;
+  if (p.sx_count * 3 > kPreMaxSpan) return fail("vfp_preprocess_frames: scale factor too large (source span of one output row exceeds 8192 bytes)");
+  // pack the tables into one host buffer -> one copy
+  std::vector<int32_t> host;
+  auto put_i = [&](const std::vector<int>& v) { size_t o = host.size(); host.insert(host.end(), v.begin(), v.end()); return o; };
+  auto put_f = [&](const std::vector<float>& v) { size_t o = host.size(); host.resize(o + v.size()); memcpy(host.data() + o, v.data(), v.size() * 4); return o; };
+  const size_t o_xb = put_i(xb), o_xs = put_i(xs), o_xa = put_f(xa), o_yb = put_i(yb), o_ys = put_i(ys), o_ya = put_f(ya);
+  if (host.size() * 4 > workspace_bytes) return fail("vfp_preprocess_frames: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int32_t* dev = static_cast<int32_t*>(workspace);
+  VFP_CUDA(cudaMemcpyAsync(dev, host.data(), host.size() * 4, cudaMemcpyHostToDevice, st));   // pageable source: staged before return
+  p.src = frames_hwc; p.dst = out_hwc64; p.H = height; p.W = width;
+  p.mode = fast ? ((isx == 2 && isy == 2) ? 2 : 1) : 0;
+  p.inv_area = (float)(1.0 / (isx * isy));
+  p.x_begin = dev + o_xb; p.x_si = dev + o_xs; p.x_alpha = reinterpret_cast<const float*>(dev + o_xa);
+  p.y_begin = dev + o_yb; p.y_si = dev + o_ys; p.y_beta = reinterpret_cast<const float*>(dev + o_ya);
+  preprocess_area_kernel<<<dim3(64, (unsigned)n_frames), 192, 0, st>>>(p);
   VFP_CUDA(cudaGetLastError());
   return 0;
 }

@@ -126,6 +126,35 @@ def topk_inner_product_device(q, db, k: int) -> Tuple[torch.Tensor, torch.Tensor
     return S, I
 
 
+def preprocess_frames_device(frames) -> torch.Tensor:
+    """Device restatement of ``_preprocess_frames`` (fingerprint.py:186-214) up to, not including, the ``/ 255`` and the
+    HWC->CHW permute (both are fused into the stem kernel): decoded frames ``(T, H, W, 3)`` uint8 (a tensor, an array or a
+    list of equally sized arrays) -> ``(T, 64, 64, 3)`` uint8 on the device, bit-exact with cv2.resize(INTER_AREA) +
+    centre crop. Feed the result to ``model.fingerprint_packed(out, [T])``."""
+    _native.require_cuda()
+    lib = _native.load()
+    if isinstance(frames, (list, tuple)):
+        frames = np.stack(frames)
+    if isinstance(frames, np.ndarray):
+        frames = torch.from_numpy(np.ascontiguousarray(frames))
+    if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
+        raise ValueError("frames must be uint8 (T, H, W, 3)")
+    if not frames.is_cuda:
+        frames = frames.cuda()
+    frames = frames.contiguous()
+    t, h, w, _ = frames.shape
+    dev = frames.device
+    with torch.cuda.device(dev):
+        out = torch.empty((t, 64, 64, 3), dtype=torch.uint8, device=dev)
+        ws = torch.empty(lib.vfp_preprocess_workspace_bytes(h, w), dtype=torch.uint8, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        for f0 in range(0, t, 65535):
+            n = min(65535, t - f0)
+            _native.check(lib.vfp_preprocess_frames(C.c_void_p(frames[f0:].data_ptr()), n, h, w, C.c_void_p(out[f0:].data_ptr()),
+                                                    C.c_void_p(ws.data_ptr()), ws.numel(), st), "vfp_preprocess_frames")
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # greedy grouping (host; sequential by definition - seeds are visited in ascending index order)
 # ----------------------------------------------------------------------------------------------
@@ -209,6 +238,21 @@ class VideoFingerprintScanner:
         """Indices of the decoded frames the reference keeps (fingerprint.py:90-101)."""
         skip = max(1, total_frames // self.max_frames) if total_frames > self.max_frames else 1
         return list(range(0, total_frames, skip))[: self.max_frames]
+
+    def _preprocess_frames(self, frames) -> torch.Tensor:
+        """fingerprint.py:186-214 on the device: decoded (H, W, 3) uint8 frames -> the (T, 3, 64, 64) float clip in [0, 1] the
+        reference returns (cv2 INTER_AREA + centre crop, bit-exact). ``extract_fingerprint_from_decoded`` skips the float
+        round trip and hands the uint8 result straight to the stem kernel."""
+        return preprocess_frames_device(frames).permute(0, 3, 1, 2).float() / 255.0
+
+    def extract_fingerprint_from_decoded(self, frames) -> Optional[np.ndarray]:
+        """Decoded frames of one video -> embedding: preprocessing and forward both on the device (fingerprint.py:232-270
+        minus the PyAV decode). Fewer than 10 frames -> None like the reference (fingerprint.py:238-240)."""
+        if len(frames) < 10:
+            return None
+        u8 = preprocess_frames_device(frames)
+        emb = self.model.fingerprint_packed(u8, [u8.shape[0]])
+        return emb[0].cpu().numpy()
 
     def extract_fingerprint_from_frames(self, clip: torch.Tensor) -> Optional[np.ndarray]:
         """clip: (T,3,64,64) preprocessed frames (what _preprocess_frames returns). <10 frames -> None."""
