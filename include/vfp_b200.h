@@ -147,9 +147,10 @@ const char* vfp_profile_stage_name(int i);
 int vfp_profile_read(double* stage_ms, int n_stages, uint64_t* launches, int reset);
 
 /* Tuning knobs for experiments (process-wide). key 0: frames per conv1+conv2 stem pass of the
- * unfused path (default 16384 = the conv pass, >= 64); key 1: 1 = fused conv1+conv2 stem kernel (default for
- * u8 / bf16 frames), 0 = two kernels (always used for fp32 frames); key 2: 1 = hang diagnosis
- * mode (see vfp_debug_hang_log), 0 = watchdog traps (default); key 3: frames per conv pass (64..16384, default 16384). */
+ * unfused path (default 16384 = the conv pass, >= 64); key 1: conv1+conv2 stem: 2 = fused, conv1 as TS-mode tcgen05 UMMA (default
+ * for u8 / bf16 frames), 1 = fused with conv1 on mma.sync, 0 = two kernels (always used for fp32 frames); key 2: 1 = hang diagnosis
+ * mode (see vfp_debug_hang_log), 0 = watchdog traps (default); key 3: frames per conv pass (64..16384, default 16384);
+ * key 5 / key 6: L2 prefetch distance in column tiles of the join / the top-k screen for databases larger than L2 (0 = off). */
 int vfp_set_tuning(int key, long long value);
 
 /* Reads and clears the device-side error word set by a kernel watchdog (0 = none). Synchronises. */

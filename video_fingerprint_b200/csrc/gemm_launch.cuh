@@ -72,6 +72,7 @@ inline GemmShape plain_shape(long long M, int N, int K, int block_n, int block_k
   s.h_mul = 0;
   s.row_resident = 0;
   s.n_segments = 1;
+  s.b_prefetch_tiles = 0;
   return s;
 }
 

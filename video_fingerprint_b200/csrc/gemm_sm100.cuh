@@ -37,6 +37,7 @@ struct GemmShape {
   // row-reducing epilogue can keep per-row state across them. Concurrent CTAs stream the same columns -> L2 reuse.
   int row_resident;
   int n_segments;
+  int b_prefetch_tiles;  // L2-prefetch the B column tile this many tiles ahead (0 = off)
   // A operand addressing
   int a_conv;           // 0: rows are GEMM rows; 1: 4-D box (C, W, H, frame) over an NHWC activation tensor
   int tiles_per_frame;  // conv: row tiles per frame (>=1) ...
@@ -199,6 +200,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               frame0[sub] = mt * shape.frames_per_tile;
             }
           }
+        }
+        // A B operand much larger than L2 (a database of >= 10^6 rows in the join) comes from HBM the first time a column
+        // tile is touched, and the ~32 CTAs that share the tile all stall on that one fetch (measured: 1 241 TFLOP/s with a
+        // 134 MB database, 852 with 512 MB). The CTA that owns the group's first row tile pulls the column tile
+        // `b_prefetch_tiles` ahead into L2 (row-resident schedule of the top-k search: every 8th row tile does, the CTAs of
+        // one column segment walk the same columns at about the same time).
+        if (shape.b_prefetch_tiles > 0 && (mts * MT) % (shape.row_resident ? 8 : shape.group_m) == 0) {
+          const int pnt = nt + shape.b_prefetch_tiles;
+          if (pnt < shape.n_tiles)
+            for (int kb = 0; kb < shape.k_blocks; ++kb) tma_prefetch_l2_2d(&tmap_b, kb * BLOCK_K, pnt * BLOCK_N);
         }
         for (int kb = 0; kb < shape.k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
