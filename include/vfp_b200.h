@@ -107,6 +107,21 @@ int vfp_topk_ip(const float* q, const float* db, int64_t n_q, int64_t n_db, int 
                 float screen_margin, float* out_s, int64_t* out_idx, uint64_t* flags_out, void* workspace,
                 size_t workspace_bytes, void* stream);
 
+/* VideoFingerprint3D, the reference's second model behind create_model("3d" | "cnn3d") (/root/reference/model.py:406-512):
+ * Conv3d(3->16, (fs,5,5), stride (fs,2,2)) / (16->32) / (32->64, temporal stride 2) / (64->128), each + BatchNorm3d(eval) +
+ * ReLU, spatial average pool, temporal Conv1d(128,128,3), attention + average pooling over time, Linear-ReLU-Linear
+ * projector, L2 normalisation. vfp3d_weights_create takes the model's named fp32 state_dict tensors (like
+ * vfp_weights_create) and its frame_stride; vfp3d_forward fingerprints n_clips clips of n_frames frames each
+ * (`frames`: device (n_clips*n_frames, 3, 64, 64) planar u8 / bf16 / fp32; T is zero-padded to a multiple of frame_stride
+ * like model.py:468-471) into `emb_out` (n_clips, D) fp32, walking the batch in as many passes as the workspace allows. */
+typedef struct vfp3d_weights vfp3d_weights;
+int vfp3d_weights_create(const vfp_tensor_desc* tensors, int n_tensors, int frame_stride, vfp3d_weights** out);
+void vfp3d_weights_destroy(vfp3d_weights* w);
+int vfp3d_weights_embedding_dim(const vfp3d_weights* w);
+size_t vfp3d_forward_workspace_bytes(const vfp3d_weights* w, int64_t clips_per_pass, int n_frames);
+int vfp3d_forward(const vfp3d_weights* w, const void* frames, int frame_dtype, int64_t n_clips, int n_frames,
+                  float* emb_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Frame preprocessing of the scanner (/root/reference/fingerprint.py:186-214 _preprocess_frames): cv2.resize(frame,
  * INTER_AREA) so that the short side becomes 64 (new size truncated with int() like the reference), then the centre
  * 64 x 64 crop. `frames_hwc`: device uint8 (n_frames, height, width, 3), all frames of one size; `out_hwc64`: device

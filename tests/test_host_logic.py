@@ -40,8 +40,7 @@ def test_default_init_reproduces_reference_init(manifest):
 def test_factory_error_behaviour():
     with pytest.raises(ValueError, match="Unknown model type"):
         vfp.create_model("nope")
-    with pytest.raises(NotImplementedError):
-        vfp.create_model("3d")
+    assert isinstance(vfp.create_model("3d"), vfp.VideoFingerprint3D)          # the reference's second model (model.py:602-607)
     m = vfp.create_model("attention", embedding_dim=128, num_attention_blocks=2, frame_stride=32)  # extra kwargs ignored
     assert m.state_dict()["final_projection.3.weight"].shape == (128, 256)
     assert not any(k.startswith("attention_blocks.2.") for k in m.state_dict())
@@ -78,7 +77,7 @@ def test_partition_and_row_blocks():
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "vfp_b200.h")).read()
-    declared = set(re.findall(r"\b(vfp_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(vfp(?:3d)?_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_native.EXPORTED_SYMBOLS)
     assert os.path.exists(_native.LIB_PATH), "build the library first: python -m video_fingerprint_b200.build"
     lib = ctypes.CDLL(_native.LIB_PATH)

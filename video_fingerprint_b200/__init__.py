@@ -10,7 +10,7 @@ Public surface (mirrors /root/reference/model.py and /root/reference/fingerprint
 
 All device work goes through libvfp_b200.so (include/vfp_b200.h); there is no CPU or PyTorch fallback.
 """
-from .model import VideoFingerprintAttention, create_model  # noqa: F401
+from .model import VideoFingerprint3D, VideoFingerprintAttention, create_model  # noqa: F401
 from .fingerprint import (  # noqa: F401
     VideoFingerprintScanner,
     group_pairs_direct,
@@ -29,6 +29,7 @@ __all__ = [
     "compute_discrimination_metrics",
     "create_model",
     "VideoFingerprintAttention",
+    "VideoFingerprint3D",
     "VideoFingerprintScanner",
     "threshold_join",
     "threshold_join_device",

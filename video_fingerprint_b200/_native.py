@@ -29,6 +29,11 @@ EXPORTED_SYMBOLS = (
     "vfp_join_threshold",
     "vfp_topk_workspace_bytes",
     "vfp_topk_ip",
+    "vfp3d_weights_create",
+    "vfp3d_weights_destroy",
+    "vfp3d_weights_embedding_dim",
+    "vfp3d_forward_workspace_bytes",
+    "vfp3d_forward",
     "vfp_preprocess_workspace_bytes",
     "vfp_preprocess_frames",
     "vfp_pair_scores",
@@ -90,6 +95,16 @@ def load() -> C.CDLL:
     lib.vfp_topk_workspace_bytes.argtypes = [i64, i64, i32]
     lib.vfp_topk_ip.restype = i32
     lib.vfp_topk_ip.argtypes = [vp, vp, i64, i64, i32, i32, f32, vp, vp, vp, vp, sz, vp]
+    lib.vfp3d_weights_create.restype = i32
+    lib.vfp3d_weights_create.argtypes = [C.POINTER(TensorDesc), i32, i32, C.POINTER(vp)]
+    lib.vfp3d_weights_destroy.restype = None
+    lib.vfp3d_weights_destroy.argtypes = [vp]
+    lib.vfp3d_weights_embedding_dim.restype = i32
+    lib.vfp3d_weights_embedding_dim.argtypes = [vp]
+    lib.vfp3d_forward_workspace_bytes.restype = sz
+    lib.vfp3d_forward_workspace_bytes.argtypes = [vp, i64, i32]
+    lib.vfp3d_forward.restype = i32
+    lib.vfp3d_forward.argtypes = [vp, vp, i32, i64, i32, vp, vp, sz, vp]
     lib.vfp_preprocess_workspace_bytes.restype = sz
     lib.vfp_preprocess_workspace_bytes.argtypes = [i32, i32]
     lib.vfp_preprocess_frames.restype = i32

@@ -13,6 +13,7 @@
 #include "gemm_launch.cuh"
 #include "join_kernels.cuh"
 #include "metrics_kernels.cuh"
+#include "model3d_kernels.cuh"
 #include "preprocess_kernels.cuh"
 #include "stem_fused_kernel.cuh"
 #include "stem_ts_kernel.cuh"
@@ -1109,6 +1110,172 @@ int vfp_preprocess_frames(const uint8_t* frames_hwc, int n_frames, int height, i
   p.y_begin = dev + o_yb; p.y_si = dev + o_ys; p.y_beta = reinterpret_cast<const float*>(dev + o_ya);
   preprocess_area_kernel<<<dim3(64, (unsigned)n_frames), 192, 0, st>>>(p);
   VFP_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// VideoFingerprint3D (model.py:406-512): the reference's second model behind create_model("3d" | "cnn3d")
+// ---------------------------------------------------------------------------------------------
+}  // extern "C"
+
+struct vfp3d_weights {
+  int fs = 0, embedding_dim = 0;
+  int kp[4] = {0, 0, 0, 0};            // padded K of the four conv GEMMs
+  __nv_bfloat16* w[4] = {nullptr, nullptr, nullptr, nullptr};   // [Np][Kp] K-major, BN folded
+  float* b[4] = {nullptr, nullptr, nullptr, nullptr};           // [Np]
+  CUtensorMap tm[4];
+  float *tc_w = nullptr, *tc_b = nullptr, *ta_w = nullptr, *ta_b = nullptr, *p0_w = nullptr, *p0_b = nullptr, *p3_w = nullptr, *p3_b = nullptr;
+  std::vector<void*> allocs;
+};
+
+namespace {
+constexpr int k3dCin[4] = {3, 16, 32, 64}, k3dCout[4] = {16, 32, 64, 128};
+constexpr int k3dCinPad[4] = {3, 32, 32, 64}, k3dNp[4] = {32, 32, 64, 128};   // channel counts as stored (padded to the 32-column store box)
+
+template <class T>
+int upload3d(vfp3d_weights* w, const std::vector<T>& host, T** dev) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, host.size() * sizeof(T));
+  if (e != cudaSuccess) return fail_cuda("cudaMalloc", e);
+  w->allocs.push_back(p);
+  e = cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail_cuda("cudaMemcpy", e);
+  *dev = static_cast<T*>(p);
+  return 0;
+}
+struct Dims3d { int G, T3; long long m[4]; };
+Dims3d dims3d(long long B, int T, int fs) {
+  Dims3d d;
+  d.G = (T + fs - 1) / fs;
+  d.T3 = (d.G - 1) / 2 + 1;
+  d.m[0] = B * d.G * 1024; d.m[1] = B * d.G * 256; d.m[2] = B * d.T3 * 64; d.m[3] = B * d.T3 * 16;
+  return d;
+}
+}  // namespace
+
+extern "C" {
+
+void vfp3d_weights_destroy(vfp3d_weights* w) {
+  if (!w) return;
+  for (void* p : w->allocs) cudaFree(p);
+  delete w;
+}
+int vfp3d_weights_embedding_dim(const vfp3d_weights* w) { return w ? w->embedding_dim : 0; }
+
+int vfp3d_weights_create(const vfp_tensor_desc* tensors, int n_tensors, int frame_stride, vfp3d_weights** out) {
+  if (!tensors || !out || n_tensors <= 0) return fail("vfp3d_weights_create: null argument");
+  if (frame_stride < 1 || frame_stride > 64) return fail("vfp3d_weights_create: frame_stride must be in [1, 64]");
+  TensorTable t;
+  for (int i = 0; i < n_tensors; ++i) t.by_name[tensors[i].name] = &tensors[i];
+  std::string err;
+  vfp3d_weights* w = new vfp3d_weights();
+  auto bail = [&](const std::string& m) {
+    vfp3d_weights_destroy(w);
+    return fail("vfp3d_weights_create: " + (m.empty() ? g_last_error : m));
+  };
+  w->fs = frame_stride;
+  for (int l = 0; l < 4; ++l) {
+    const std::string pre = "encoder." + std::to_string(l);
+    const int kt = l == 0 ? frame_stride : 3, ks = l == 0 ? 5 : 3, cin = k3dCin[l], cout = k3dCout[l], cpad = k3dCinPad[l];
+    const int taps = kt * ks * ks;
+    const float* cw = t.get(pre + ".conv.weight", (int64_t)cout * cin * taps, &err);
+    const float* cb = cw ? t.get(pre + ".conv.bias", cout, &err) : nullptr;
+    if (!cb) return bail(err);
+    // eval-mode BatchNorm3d folded (the tensors are named .bn.* here, not encoder.N like the attention model)
+    BnFold bn;
+    if (!load_bn(t, pre + ".bn", cout, &bn, &err)) return bail(err);
+    const int kreal = taps * cpad;
+    w->kp[l] = (kreal + 63) / 64 * 64;
+    std::vector<float> wf((size_t)k3dNp[l] * w->kp[l], 0.0f), bf(k3dNp[l], 0.0f);
+    for (int co = 0; co < cout; ++co) {
+      for (int c = 0; c < cin; ++c)
+        for (int tap = 0; tap < taps; ++tap)   // reference layout (cout, cin, kt, kh, kw); ours k = tap * cpad + c, tap = (kt*ks + kh)*ks + kw
+          wf[(size_t)co * w->kp[l] + (size_t)tap * cpad + c] = cw[((size_t)co * cin + c) * taps + tap] * bn.scale[co];
+      bf[co] = cb[co] * bn.scale[co] + bn.shift[co];
+    }
+    if (upload3d(w, to_bf16(wf), &w->w[l]) || upload3d(w, bf, &w->b[l])) return bail("");
+    if (make_tmap_rows_bf16(&w->tm[l], w->w[l], (uint64_t)k3dNp[l], (uint64_t)w->kp[l], (uint64_t)w->kp[l], (uint32_t)std::min(k3dNp[l], 256), 64))
+      return bail("tensor map encode failed");
+  }
+  auto f32 = [&](const std::string& name, int64_t n, float** dev) -> bool {
+    const float* src = t.get(name, n, &err);
+    if (!src) return false;
+    std::vector<float> h(src, src + n);
+    return upload3d(w, h, dev) == 0;
+  };
+  const int64_t d = t.numel("projector.3.bias");
+  if (d <= 0 || d > 512) return bail("projector.3.bias missing or embedding_dim > 512");
+  w->embedding_dim = (int)d;
+  if (!f32("temporal_conv.weight", 128 * 128 * 3, &w->tc_w) || !f32("temporal_conv.bias", 128, &w->tc_b) ||
+      !f32("temporal_attention.weight", 128, &w->ta_w) || !f32("temporal_attention.bias", 1, &w->ta_b) ||
+      !f32("projector.0.weight", 128 * 128, &w->p0_w) || !f32("projector.0.bias", 128, &w->p0_b) ||
+      !f32("projector.3.weight", d * 128, &w->p3_w) || !f32("projector.3.bias", d, &w->p3_b))
+    return bail(err);
+  *out = w;
+  return 0;
+}
+
+size_t vfp3d_forward_workspace_bytes(const vfp3d_weights* w, int64_t clips_per_pass, int n_frames) {
+  if (!w || clips_per_pass <= 0 || n_frames <= 0) return 0;
+  const Dims3d d = dims3d(clips_per_pass, n_frames, w->fs);
+  size_t a = 0, act = 0;
+  for (int l = 0; l < 4; ++l) {
+    a = std::max(a, align_up((size_t)d.m[l] * w->kp[l] * 2, 1024));
+    act += align_up((size_t)d.m[l] * k3dNp[l] * 2, 1024);
+  }
+  return a + act + 1024;
+}
+
+int vfp3d_forward(const vfp3d_weights* w, const void* frames, int frame_dtype, int64_t n_clips, int n_frames, float* emb_out,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (!w || !frames || !emb_out || !workspace) return fail("vfp3d_forward: null argument");
+  if (n_clips <= 0 || n_frames <= 0) return fail("vfp3d_forward: empty input");
+  if (frame_dtype != VFP_FRAME_U8 && frame_dtype != VFP_FRAME_BF16 && frame_dtype != VFP_FRAME_F32) return fail("vfp3d_forward: planar u8 / bf16 / fp32 frames only");
+  const Dims3d one = dims3d(1, n_frames, w->fs);
+  if (one.T3 > kHead3dMaxT) return fail("vfp3d_forward: clip too long (more than 32 temporal positions after the strides)");
+  // largest pass that fits the workspace
+  int64_t per = n_clips;
+  while (per > 1 && vfp3d_forward_workspace_bytes(w, per, n_frames) > workspace_bytes) per = (per + 1) / 2;
+  if (vfp3d_forward_workspace_bytes(w, per, n_frames) > workspace_bytes) return fail("vfp3d_forward: workspace too small for one clip; see vfp3d_forward_workspace_bytes");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t frame_bytes = (size_t)12288 * (frame_dtype == VFP_FRAME_BF16 ? 2 : frame_dtype == VFP_FRAME_F32 ? 4 : 1);
+  for (int64_t c0 = 0; c0 < n_clips; c0 += per) {
+    const int64_t B = std::min<int64_t>(per, n_clips - c0);
+    const Dims3d d = dims3d(B, n_frames, w->fs);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    size_t a_bytes = 0;
+    for (int l = 0; l < 4; ++l) a_bytes = std::max(a_bytes, align_up((size_t)d.m[l] * w->kp[l] * 2, 1024));
+    __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* act[4];
+    size_t off = a_bytes;
+    for (int l = 0; l < 4; ++l) { act[l] = reinterpret_cast<__nv_bfloat16*>(ws + off); off += align_up((size_t)d.m[l] * k3dNp[l] * 2, 1024); }
+    const uint8_t* fr = static_cast<const uint8_t*>(frames) + (size_t)c0 * n_frames * frame_bytes;
+    for (int l = 0; l < 4; ++l) {
+      const long long items = d.m[l] * (w->kp[l] / 8);
+      const unsigned grid = (unsigned)std::min<long long>((items + 255) / 256, (long long)device_sm_count() * 32);
+      if (l == 0) {
+        im2col3d_frames_kernel<<<grid, 256, 0, st>>>(fr, frame_dtype, (int)B, n_frames, w->fs, d.G, w->kp[0], A);
+      } else {
+        const int Ti = l == 3 ? d.T3 : d.G, Hi = 64 >> l, st_t = l == 2 ? 2 : 1, To = l == 1 ? d.G : d.T3;
+        im2col3d_ndhwc_kernel<<<grid, 256, 0, st>>>(act[l - 1], (int)B, Ti, Hi, Hi, k3dCinPad[l], st_t, To, Hi / 2, Hi / 2, w->kp[l], A);
+      }
+      CUtensorMap ta;
+      if (make_tmap_rows_bf16(&ta, A, (uint64_t)d.m[l], (uint64_t)w->kp[l], (uint64_t)w->kp[l], 128, 64)) return fail("vfp3d_forward: tensor map encode failed (A)");
+      EpiBiasActTma<true>::Params ep{};
+      if (make_tmap_out(&ep.tmap_out, act[l], (uint64_t)d.m[l], (uint64_t)k3dNp[l], true)) return fail("vfp3d_forward: tensor map encode failed (out)");
+      ep.bias = w->b[l]; ep.N = k3dNp[l]; ep.act = 1;
+      GemmShape s = plain_shape(d.m[l], k3dNp[l], w->kp[l], k3dNp[l], 64, 32);
+      if (l <= 1) VFP_CUDA((launch_gemm<32, 64, 4, EpiBiasActTma<true>>(ta, w->tm[l], s, ep, st)));
+      else if (l == 2) VFP_CUDA((launch_gemm<64, 64, 4, EpiBiasActTma<true>>(ta, w->tm[l], s, ep, st)));
+      else VFP_CUDA((launch_gemm<128, 64, 4, EpiBiasActTma<true>>(ta, w->tm[l], s, ep, st)));
+    }
+    Head3dParams hp{};
+    hp.act = act[3]; hp.T3 = d.T3; hp.tc_w = w->tc_w; hp.tc_b = w->tc_b; hp.ta_w = w->ta_w; hp.ta_b = w->ta_b;
+    hp.p0_w = w->p0_w; hp.p0_b = w->p0_b; hp.p3_w = w->p3_w; hp.p3_b = w->p3_b; hp.D = w->embedding_dim;
+    hp.out = emb_out + (size_t)c0 * w->embedding_dim;
+    head3d_kernel<<<(unsigned)B, 128, 0, st>>>(hp);
+    VFP_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

@@ -223,6 +223,132 @@ class VideoFingerprintAttention(nn.Module):
         raise NotImplementedError("training (model.py:300-390) is outside the B200 inference hot path")
 
 
+class Conv3DBlock(_ParamsOnly):
+    """Parameter layout of model.py:393-403: `conv` (Conv3d), `bn` (BatchNorm3d)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0):
+        super().__init__()
+        self.conv = nn.Conv3d(in_channels, out_channels, kernel_size, stride, padding)
+        self.bn = nn.BatchNorm3d(out_channels)
+        self.relu = nn.ReLU(inplace=True)
+
+
+class VideoFingerprint3D(nn.Module):
+    """The reference's 3-D CNN fingerprint model (model.py:406-512), inference only: same constructor arguments, same
+    state_dict keys / shapes / default initialisation, same forward contract ((B,T,3,64,64) or (B,3,T,64,64) in [0,1] ->
+    unit-norm (B, embedding_dim)); the compute is `vfp3d_forward` in libvfp_b200.so (im2col + tcgen05 GEMMs + a fused tail)."""
+
+    def __init__(self, embedding_dim=256, frame_stride=32, dropout=0.2):
+        super().__init__()
+        self.frame_stride = frame_stride
+        self.embedding_dim = embedding_dim
+        self.encoder = nn.Sequential(
+            Conv3DBlock(3, 16, kernel_size=(frame_stride, 5, 5), stride=(frame_stride, 2, 2), padding=(0, 2, 2)),
+            Conv3DBlock(16, 32, kernel_size=(3, 3, 3), stride=(1, 2, 2), padding=(1, 1, 1)),
+            Conv3DBlock(32, 64, kernel_size=(3, 3, 3), stride=(2, 2, 2), padding=(1, 1, 1)),
+            Conv3DBlock(64, 128, kernel_size=(3, 3, 3), stride=(1, 2, 2), padding=(1, 1, 1)),
+            nn.AdaptiveAvgPool3d((None, 1, 1)),
+        )
+        self.temporal_conv = nn.Conv1d(128, 128, kernel_size=3, padding=1)
+        self.temporal_attention = nn.Conv1d(128, 1, kernel_size=1)
+        self.projector = nn.Sequential(nn.Linear(128, 128), nn.ReLU(inplace=True), nn.Dropout(dropout), nn.Linear(128, embedding_dim))
+        self.temperature = nn.Parameter(torch.ones(1) * 0.07)
+        self._initialize_weights()
+        self.clips_per_pass = 64     # workspace: the explicit im2col of layer 1 is ~2.4 KB per output position
+        self._native_weights: Optional[int] = None
+        self._native_key: Optional[tuple] = None
+        self._workspace: Optional[torch.Tensor] = None
+
+    def _initialize_weights(self):
+        """model.py:454-466 (same module order, so a fixed torch.manual_seed gives the reference's initial weights)."""
+        for m in self.modules():
+            if isinstance(m, nn.Conv3d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.BatchNorm3d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.Linear):
+                nn.init.normal_(m.weight, 0, 0.01)
+                nn.init.constant_(m.bias, 0)
+
+    def _weights_key(self) -> tuple:
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def _release_native(self) -> None:
+        if self._native_weights is not None:
+            try:
+                _native.load().vfp3d_weights_destroy(C.c_void_p(self._native_weights))
+            except Exception:  # pragma: no cover - interpreter teardown
+                pass
+            self._native_weights = None
+            self._native_key = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self._release_native()
+        except Exception:
+            pass
+
+    def _ensure_native(self) -> int:
+        key = self._weights_key()
+        if self._native_weights is not None and key == self._native_key:
+            return self._native_weights
+        self._release_native()
+        lib = _native.load()
+        host = {k: v.detach().to("cpu").contiguous() for k, v in self.state_dict().items()}
+        host = {k: (v.float() if v.is_floating_point() else v) for k, v in host.items()}
+        descs = (_native.TensorDesc * len(host))()
+        for i, (k, v) in enumerate(host.items()):
+            descs[i] = _native.TensorDesc(k.encode(), v.data_ptr(), v.numel())
+        handle = C.c_void_p()
+        _native.check(lib.vfp3d_weights_create(descs, len(host), int(self.frame_stride), C.byref(handle)), "vfp3d_weights_create")
+        self._native_weights = handle.value
+        self._native_key = key
+        return self._native_weights
+
+    @torch.no_grad()
+    def forward(self, video: torch.Tensor):
+        """model.py:468-509: (B,T,3,H,W) is detected by `shape[2] == 3`, anything else is taken as (B,3,T,H,W)."""
+        _native.require_cuda()
+        if self.training:
+            raise RuntimeError("inference only: call .eval() first")
+        if video.dim() != 5:
+            raise ValueError(f"expected a 5-D video tensor, got shape {tuple(video.shape)}")
+        if video.shape[2] != 3:      # (B, C, T, H, W) -> (B, T, C, H, W): the kernels read per-frame planar images
+            video = video.permute(0, 2, 1, 3, 4)
+        B, T = int(video.shape[0]), int(video.shape[1])
+        if tuple(video.shape[2:]) != (3, 64, 64):
+            raise ValueError("the sm_100a kernels are specialised for 3 x 64 x 64 frames")
+        if not video.is_cuda:
+            video = video.cuda()
+        if video.dtype == torch.uint8:
+            code = _native.FRAME_U8
+        elif video.dtype == torch.bfloat16:
+            code = _native.FRAME_BF16
+        else:
+            code, video = _native.FRAME_F32, video.float()
+        frames = video.contiguous()
+        dev = frames.device
+        lib = _native.load()
+        with torch.cuda.device(dev):
+            weights = self._ensure_native()
+            per = max(1, min(B, self.clips_per_pass))
+            nbytes = lib.vfp3d_forward_workspace_bytes(C.c_void_p(weights), per, T)
+            if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != dev:
+                self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            emb = torch.empty((B, self.embedding_dim), dtype=torch.float32, device=dev)
+            rc = lib.vfp3d_forward(C.c_void_p(weights), C.c_void_p(frames.data_ptr()), code, B, T, C.c_void_p(emb.data_ptr()),
+                                   C.c_void_p(self._workspace.data_ptr()), self._workspace.numel(),
+                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _native.check(rc, "vfp3d_forward")
+        return emb
+
+    def compute_loss(self, *a, **k):
+        raise NotImplementedError("training (model.py:514-582) is outside the B200 inference hot path")
+
+
 def create_model(model_type: str = "attention", **kwargs) -> nn.Module:
     """Factory with the reference's signature and error behaviour (model.py:585-610)."""
     if model_type == "attention":
@@ -233,5 +359,9 @@ def create_model(model_type: str = "attention", **kwargs) -> nn.Module:
             num_attention_blocks=kwargs.get("num_attention_blocks", 4),
         )
     if model_type in ("3d", "cnn3d"):
-        raise NotImplementedError("the 3-D CNN model (model.py:393-582) is outside the B200 hot path (SURVEY.md section 8f)")
+        return VideoFingerprint3D(
+            embedding_dim=kwargs.get("embedding_dim", 256),
+            frame_stride=kwargs.get("frame_stride", 16),
+            dropout=kwargs.get("dropout", 0.2),
+        )
     raise ValueError(f"Unknown model type: {model_type}")
