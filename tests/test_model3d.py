@@ -99,3 +99,25 @@ def test_device_forward_dtypes_layouts_and_passes():
     assert torch.equal(m(clips.cuda()).cpu(), e_f32)
     with pytest.raises(_native.NativeError):
         m(torch.zeros(1, 16 * 2 * 33, 3, 64, 64))                              # more than 32 temporal positions
+
+
+@pytest.mark.gpu
+def test_scanner_3d_window_semantics():
+    """fingerprint.py:272-320: short video = one clip; long video = 3..5 windows of clip_length frames, mean, re-normalise."""
+    import video_fingerprint_b200 as vfp
+
+    fs = 16
+    sd = fo.make_state_dict_3d(21, fs)
+    m = vfp.create_model("3d", frame_stride=fs).eval()
+    m.load_state_dict(sd)
+    scanner = vfp.VideoFingerprintScanner(model=m, config={"model_type": "3d", "clip_length": 32, "frame_stride": fs})
+    assert scanner.window_starts_3d(30) == [0] and scanner.window_starts_3d(100) == [0, 34, 68] and len(scanner.window_starts_3d(400)) == 5
+    video = fo.make_clips_3d(7, 1, 100)[0]                  # (100, 3, 64, 64)
+    got = scanner.extract_fingerprint_3d_from_frames(video.cuda())
+    embs = torch.cat([fo.forward3d_oracle(sd, video[s : s + 32].unsqueeze(0), fs) for s in (0, 34, 68)]).numpy()
+    want = embs.mean(axis=0)
+    want = want / np.linalg.norm(want)
+    assert float(cosine(got, want)) >= COS_BAR
+    short = scanner.extract_fingerprint_3d_from_frames(video[:20].cuda())
+    assert float(cosine(short, fo.forward3d_oracle(sd, video[:20].unsqueeze(0), fs)[0])) >= COS_BAR
+    assert scanner.extract_fingerprint_3d_from_frames(video[:9].cuda()) is None

@@ -17,37 +17,80 @@ namespace vfp {
 
 // Layer 1: Conv3d(3 -> 16, kernel (fs, 5, 5), stride (fs, 2, 2), padding (0, 2, 2)) over planar frames (B*T, 3, 64, 64) of any
 // accepted dtype; T is zero-padded to a multiple of fs like model.py:468-471. Row = (b, g, oh, ow) with 32 x 32 output
-// positions per group of fs frames; column k = ((kt*5 + kh)*5 + kw)*3 + c, zero-filled up to `kp`.
-__global__ void im2col3d_frames_kernel(const void* __restrict__ frames, int frame_dtype, int B, int T, int fs, int groups,
-                                       int kp, __nv_bfloat16* __restrict__ out) {
-  const long long rows = (long long)B * groups * 1024;
-  const int k8n = kp / 8;
-  const long long total = rows * k8n;
-  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
-    const long long row = it / k8n;
-    const int k0 = (int)(it - row * k8n) * 8;
-    const int ow = (int)(row & 31), oh = (int)((row >> 5) & 31);
-    const long long bg = row >> 10;
-    const int g = (int)(bg % groups);
-    const long long b = bg / groups;
-    __align__(16) __nv_bfloat16 v[8];
+// positions per group of fs frames. K is laid out like the attention model's conv1: per (kt, kh) a run of 16 values = the 5 x 3
+// (kw, c) taps, which are 15 CONSECUTIVE bf16 of a pixel-interleaved (HWC) copy of the input row, + 1 don't-care (zero weight):
+// k = (kt*5 + kh)*16 + kw*3 + c, K = 80 * fs (a multiple of 64 for even fs... padded to `kp` otherwise).
+// One CTA per (b, g, oh): the 5 input rows x fs frames that output row needs are staged in shared memory as HWC bf16 (68 pixels:
+// zero halo of 2 on both sides; rows outside the image and frames past the clip end are zero), then every thread copies runs:
+// 8 aligned 32-bit shared loads -> two 16-byte global stores, consecutive threads = consecutive runs of one output position
+// (coalesced 1 KB per warp).
+__global__ void __launch_bounds__(256) im2col3d_frames_kernel(const void* __restrict__ frames, int frame_dtype, int T, int fs,
+                                                              int groups, int kp, __nv_bfloat16* __restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem3d[];
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(smem3d);   // [fs*5 runs][68 pixels][3 channels] (+ 2 pad elements)
+  const int oh = blockIdx.x & 31;
+  const int g = (blockIdx.x >> 5) % groups;
+  const long long b = (blockIdx.x >> 5) / groups;
+  const int tid = threadIdx.x;
+  const int runs = fs * 5;
+  // halo pixels (x = -2, -1, 64, 65) of every run
+  for (int i = tid; i < runs * 12; i += 256) {
+    const int run = i / 12, r = i - run * 12;
+    const int x = r < 6 ? r / 3 : 66 + (r - 6) / 3, c = r % 3;
+    tile[(run * 68 + x) * 3 + c] = __float2bfloat16(0.0f);
+  }
+  // load: one item = 8 consecutive pixels of one (run, plane) row: a 16-byte (bf16) / 8-byte (u8) / 32-byte (fp32) load
+  for (int i = tid; i < runs * 24; i += 256) {
+    const int x0 = (i & 7) * 8, c = (i >> 3) % 3, run = i / 24;
+    const int kh = run % 5, kt = run / 5;
+    const int t = g * fs + kt, ih = 2 * oh + kh - 2;
+    float v[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = k0 + e;
-      float x = 0.0f;
-      if (k < fs * 75) {
-        const int c = k % 3, kw = (k / 3) % 5, kh = (k / 15) % 5, kt = k / 75;
-        const int t = g * fs + kt, ih = 2 * oh + kh - 2, iw = 2 * ow + kw - 2;
-        if (t < T && ih >= 0 && ih < 64 && iw >= 0 && iw < 64) {
-          const size_t idx = (((size_t)(b * T + t) * 3 + c) * 64 + ih) * 64 + iw;
-          if (frame_dtype == kFrameU8) x = (float)static_cast<const uint8_t*>(frames)[idx] * (1.0f / 255.0f);
-          else if (frame_dtype == kFrameBF16) x = __bfloat162float(static_cast<const __nv_bfloat16*>(frames)[idx]);
-          else x = static_cast<const float*>(frames)[idx];
+    for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    if (t < T && ih >= 0 && ih < 64) {
+      const size_t idx = (((size_t)(b * T + t) * 3 + c) * 64 + ih) * 64 + x0;
+      if (frame_dtype == kFrameBF16) {
+        const uint4 q = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(frames) + idx);
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[2 * j] = __uint_as_float(w[j] << 16);
+          v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
         }
+      } else if (frame_dtype == kFrameU8) {
+        const uint2 q = *reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(frames) + idx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[j] = (float)((q.x >> (8 * j)) & 0xFF) * (1.0f / 255.0f);
+          v[4 + j] = (float)((q.y >> (8 * j)) & 0xFF) * (1.0f / 255.0f);
+        }
+      } else {
+        const float4 a = *reinterpret_cast<const float4*>(static_cast<const float*>(frames) + idx);
+        const float4 d = *reinterpret_cast<const float4*>(static_cast<const float*>(frames) + idx + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = d.x; v[5] = d.y; v[6] = d.z; v[7] = d.w;
       }
-      v[e] = __float2bfloat16(x);
     }
-    *reinterpret_cast<uint4*>(out + row * kp + k0) = *reinterpret_cast<const uint4*>(v);
+    __nv_bfloat16* dst = tile + (run * 68 + x0 + 2) * 3 + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[3 * j] = __float2bfloat16(v[j]);
+  }
+  if (tid < 2) tile[runs * 204 + tid] = __float2bfloat16(0.0f);   // the don't-care element after the very last run
+  __syncthreads();
+  // runs beyond fs*5 (K padding up to kp) are zero
+  const int kruns = kp / 16;
+  __nv_bfloat16* orow = out + ((size_t)(b * groups + g) * 1024 + (size_t)oh * 32) * kp;
+  const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
+  for (int it = tid; it < 32 * kruns; it += 256) {
+    const int ow = it / kruns, run = it - ow * kruns;
+    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
+    if (run < runs) {
+      const uint32_t* src = tile32 + run * 102 + 3 * ow;   // element (run*68 + 2*ow)*3 = word run*102 + 3*ow
+      lo = make_uint4(src[0], src[1], src[2], src[3]);
+      hi = make_uint4(src[4], src[5], src[6], src[7]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(orow + (size_t)ow * kp + run * 16);
+    dst[0] = lo;
+    dst[1] = hi;
   }
 }
 

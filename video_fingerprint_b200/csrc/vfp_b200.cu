@@ -1184,13 +1184,16 @@ int vfp3d_weights_create(const vfp_tensor_desc* tensors, int n_tensors, int fram
     // eval-mode BatchNorm3d folded (the tensors are named .bn.* here, not encoder.N like the attention model)
     BnFold bn;
     if (!load_bn(t, pre + ".bn", cout, &bn, &err)) return bail(err);
-    const int kreal = taps * cpad;
+    // layer 0: per (kt, kh) a run of 16 = (kw, c) taps + 1 zero (im2col3d_frames_kernel); layers 1-3: k = tap * cpad + c
+    const int kreal = l == 0 ? kt * 5 * 16 : taps * cpad;
     w->kp[l] = (kreal + 63) / 64 * 64;
     std::vector<float> wf((size_t)k3dNp[l] * w->kp[l], 0.0f), bf(k3dNp[l], 0.0f);
     for (int co = 0; co < cout; ++co) {
       for (int c = 0; c < cin; ++c)
-        for (int tap = 0; tap < taps; ++tap)   // reference layout (cout, cin, kt, kh, kw); ours k = tap * cpad + c, tap = (kt*ks + kh)*ks + kw
-          wf[(size_t)co * w->kp[l] + (size_t)tap * cpad + c] = cw[((size_t)co * cin + c) * taps + tap] * bn.scale[co];
+        for (int tap = 0; tap < taps; ++tap) {   // reference layout (cout, cin, kt, kh, kw), tap = (kt*ks + kh)*ks + kw
+          const size_t k = l == 0 ? (size_t)(tap / 5) * 16 + (size_t)(tap % 5) * 3 + c : (size_t)tap * cpad + c;
+          wf[(size_t)co * w->kp[l] + k] = cw[((size_t)co * cin + c) * taps + tap] * bn.scale[co];
+        }
       bf[co] = cb[co] * bn.scale[co] + bn.shift[co];
     }
     if (upload3d(w, to_bf16(wf), &w->w[l]) || upload3d(w, bf, &w->b[l])) return bail("");
@@ -1254,7 +1257,13 @@ int vfp3d_forward(const vfp3d_weights* w, const void* frames, int frame_dtype, i
       const long long items = d.m[l] * (w->kp[l] / 8);
       const unsigned grid = (unsigned)std::min<long long>((items + 255) / 256, (long long)device_sm_count() * 32);
       if (l == 0) {
-        im2col3d_frames_kernel<<<grid, 256, 0, st>>>(fr, frame_dtype, (int)B, n_frames, w->fs, d.G, w->kp[0], A);
+        const size_t smem = (size_t)w->fs * 5 * 204 * 2 + 16;
+        static bool configured = false;
+        if (!configured) {
+          VFP_CUDA(cudaFuncSetAttribute(im2col3d_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 5 * 204 * 2 + 16));
+          configured = true;
+        }
+        im2col3d_frames_kernel<<<(unsigned)(B * d.G * 32), 256, smem, st>>>(fr, frame_dtype, n_frames, w->fs, d.G, w->kp[0], A);
       } else {
         const int Ti = l == 3 ? d.T3 : d.G, Hi = 64 >> l, st_t = l == 2 ? 2 : 1, To = l == 1 ? d.G : d.T3;
         im2col3d_ndhwc_kernel<<<grid, 256, 0, st>>>(act[l - 1], (int)B, Ti, Hi, Hi, k3dCinPad[l], st_t, To, Hi / 2, Hi / 2, w->kp[l], A);

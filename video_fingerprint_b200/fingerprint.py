@@ -254,6 +254,31 @@ class VideoFingerprintScanner:
         emb = self.model.fingerprint_packed(u8, [u8.shape[0]])
         return emb[0].cpu().numpy()
 
+    def window_starts_3d(self, total_frames: int) -> List[int]:
+        """Start frames of the clip_length windows the 3-D scanner path fingerprints (fingerprint.py:293-303); one window
+        starting at 0 (taking every frame) when the video is not longer than clip_length (fingerprint.py:280-291)."""
+        clip_length = self.config.get("clip_length", 128)
+        if total_frames <= clip_length:
+            return [0]
+        num_windows = min(5, max(3, total_frames // (clip_length * 2)))
+        stride = (total_frames - clip_length) // (num_windows - 1) if num_windows > 1 else 0
+        return [i * stride for i in range(num_windows)]
+
+    def extract_fingerprint_3d_from_frames(self, frames: torch.Tensor) -> Optional[np.ndarray]:
+        """3-D model path of the scanner (fingerprint.py:272-320) on preprocessed frames (T, 3, 64, 64): < 10 frames -> None;
+        a video of at most clip_length frames is one clip; longer ones are 3..5 windows of clip_length frames whose embeddings
+        are averaged and re-normalised. All windows go through ONE batched forward."""
+        total = int(frames.shape[0])
+        if total < 10:
+            return None
+        clip_length = self.config.get("clip_length", 128)
+        if total <= clip_length:
+            return self.model(frames.unsqueeze(0))[0].cpu().numpy()
+        windows = torch.stack([frames[s : s + clip_length] for s in self.window_starts_3d(total)])
+        emb = self.model(windows).cpu().numpy()
+        final = np.mean(emb, axis=0)
+        return final / np.linalg.norm(final)
+
     def extract_fingerprint_from_frames(self, clip: torch.Tensor) -> Optional[np.ndarray]:
         """clip: (T,3,64,64) preprocessed frames (what _preprocess_frames returns). <10 frames -> None."""
         out = self.extract_fingerprints_from_frames([clip])
