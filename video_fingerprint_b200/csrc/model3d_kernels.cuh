@@ -15,35 +15,41 @@
 
 namespace vfp {
 
-// Layer 1: Conv3d(3 -> 16, kernel (fs, 5, 5), stride (fs, 2, 2), padding (0, 2, 2)) over planar frames (B*T, 3, 64, 64) of any
-// accepted dtype; T is zero-padded to a multiple of fs like model.py:468-471. Row = (b, g, oh, ow) with 32 x 32 output
-// positions per group of fs frames. K is laid out like the attention model's conv1: per (kt, kh) a run of 16 values = the 5 x 3
-// (kw, c) taps, which are 15 CONSECUTIVE bf16 of a pixel-interleaved (HWC) copy of the input row, + 1 don't-care (zero weight):
-// k = (kt*5 + kh)*16 + kw*3 + c, K = 80 * fs (a multiple of 64 for even fs... padded to `kp` otherwise).
-// One CTA per (b, g, oh): the 5 input rows x fs frames that output row needs are staged in shared memory as HWC bf16 (68 pixels:
-// zero halo of 2 on both sides; rows outside the image and frames past the clip end are zero), then every thread copies runs:
-// 8 aligned 32-bit shared loads -> two 16-byte global stores, consecutive threads = consecutive runs of one output position
-// (coalesced 1 KB per warp).
-__global__ void __launch_bounds__(256) im2col3d_frames_kernel(const void* __restrict__ frames, int frame_dtype, int T, int fs,
-                                                              int groups, int kp, __nv_bfloat16* __restrict__ out) {
+// Layer 1: Conv3d(3 -> 16, kernel (fs, 5, 5), stride (fs, 2, 2), padding (0, 2, 2)) + folded BatchNorm3d + ReLU over planar
+// frames (B*T, 3, 64, 64) of any accepted dtype; T is zero-padded to a multiple of fs like model.py:468-471.
+// C_in = 3 makes this the same problem as the attention model's conv1 (6-byte pixels are not TMA / UMMA addressable), with
+// the same answer: the register-fragment tensor path. Per (kt, kh) the 5 x 3 (kw, c) taps of an output position are 15
+// CONSECUTIVE bf16 of a pixel-interleaved (HWC) copy of the input row (+ 1 don't-care with zero weight), so one A register of
+// mma.sync m16n8k16 is one aligned 32-bit shared load: K = 16 * 5 * fs, k = (kt*5 + kh)*16 + kw*3 + c.
+// One CTA per (b, g, oh) = 32 output positions x 16 channels: the 5 input rows x fs frames it needs are staged in shared memory
+// (68 pixels: zero halo of 2 on both sides; rows outside the image and frames past the clip end are zero), the four warps
+// split the 5*fs K runs, partial sums meet in shared memory, bias + ReLU, bf16 channels-last output [position][32] (channels
+// 16..31 zero: the 32-column box of the next layer's GEMM). An earlier version materialised the im2col matrix (2.6 GB written
+// and read back per 256 clips): 1.05 ms per 256 clips against 0.1 ms here.
+// wpack: [5*fs runs][2 n-tiles][32 lanes] x uint2 = the B fragments of the folded weights; bias [16].
+__global__ void __launch_bounds__(128) conv3d_l1_kernel(const void* __restrict__ frames, int frame_dtype, int T, int fs, int groups,
+                                                        const uint2* __restrict__ wpack, const float* __restrict__ bias,
+                                                        __nv_bfloat16* __restrict__ out) {
   extern __shared__ __align__(16) uint8_t smem3d[];
   __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(smem3d);   // [fs*5 runs][68 pixels][3 channels] (+ 2 pad elements)
-  const int oh = blockIdx.x & 31;
-  const int g = (blockIdx.x >> 5) % groups;
-  const long long b = (blockIdx.x >> 5) / groups;
-  const int tid = threadIdx.x;
   const int runs = fs * 5;
+  float* part = reinterpret_cast<float*>(smem3d + (((size_t)runs * 204 * 2 + 4 + 15) & ~size_t(15)));   // [4 warps][16][32 lanes]
+  const int oh = blockIdx.x & 31;
+  const int g_idx = (blockIdx.x >> 5) % groups;
+  const long long b = (blockIdx.x >> 5) / groups;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // halo pixels (x = -2, -1, 64, 65) of every run
-  for (int i = tid; i < runs * 12; i += 256) {
+  for (int i = tid; i < runs * 12; i += 128) {
     const int run = i / 12, r = i - run * 12;
     const int x = r < 6 ? r / 3 : 66 + (r - 6) / 3, c = r % 3;
     tile[(run * 68 + x) * 3 + c] = __float2bfloat16(0.0f);
   }
+  if (tid < 2) tile[runs * 204 + tid] = __float2bfloat16(0.0f);   // the don't-care element after the very last run
   // load: one item = 8 consecutive pixels of one (run, plane) row: a 16-byte (bf16) / 8-byte (u8) / 32-byte (fp32) load
-  for (int i = tid; i < runs * 24; i += 256) {
+  for (int i = tid; i < runs * 24; i += 128) {
     const int x0 = (i & 7) * 8, c = (i >> 3) % 3, run = i / 24;
     const int kh = run % 5, kt = run / 5;
-    const int t = g * fs + kt, ih = 2 * oh + kh - 2;
+    const int t = g_idx * fs + kt, ih = 2 * oh + kh - 2;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.0f;
@@ -74,24 +80,58 @@ __global__ void __launch_bounds__(256) im2col3d_frames_kernel(const void* __rest
 #pragma unroll
     for (int j = 0; j < 8; ++j) dst[3 * j] = __float2bfloat16(v[j]);
   }
-  if (tid < 2) tile[runs * 204 + tid] = __float2bfloat16(0.0f);   // the don't-care element after the very last run
   __syncthreads();
-  // runs beyond fs*5 (K padding up to kp) are zero
-  const int kruns = kp / 16;
-  __nv_bfloat16* orow = out + ((size_t)(b * groups + g) * 1024 + (size_t)oh * 32) * kp;
+  // ---- this warp's share of the K runs: 2 m-tiles (positions 0-15, 16-31) x 2 n-tiles (channels 0-7, 8-15) ----
+  const int g = lane >> 2, tig = lane & 3;
   const uint32_t* tile32 = reinterpret_cast<const uint32_t*>(tile);
-  for (int it = tid; it < 32 * kruns; it += 256) {
-    const int ow = it / kruns, run = it - ow * kruns;
-    uint4 lo = make_uint4(0u, 0u, 0u, 0u), hi = lo;
-    if (run < runs) {
-      const uint32_t* src = tile32 + run * 102 + 3 * ow;   // element (run*68 + 2*ow)*3 = word run*102 + 3*ow
-      lo = make_uint4(src[0], src[1], src[2], src[3]);
-      hi = make_uint4(src[4], src[5], src[6], src[7]);
+  float acc[2][2][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.0f;
+  for (int run = warp; run < runs; run += 4) {
+    const uint2 b0 = __ldg(wpack + (run * 2 + 0) * 32 + lane), b1 = __ldg(wpack + (run * 2 + 1) * 32 + lane);
+    const uint32_t bf0[2] = {b0.x, b0.y}, bf1[2] = {b1.x, b1.y};
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      // element (run*68 + 2*ow)*3 + k of the tile = word run*102 + 3*ow + k/2; fragment rows are positions ow = 16*mt + g, + 8
+      const uint32_t* base = tile32 + run * 102 + 3 * (16 * mt + g) + tig;
+      uint32_t a[4];
+      a[0] = base[0];
+      a[1] = base[24];
+      a[2] = base[4];
+      a[3] = base[28];
+      mma_bf16_16816(acc[mt][0], a, bf0);
+      mma_bf16_16816(acc[mt][1], a, bf1);
     }
-    uint4* dst = reinterpret_cast<uint4*>(orow + (size_t)ow * kp + run * 16);
-    dst[0] = lo;
-    dst[1] = hi;
   }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) part[(warp * 16 + (mt * 2 + nt) * 4 + i) * 32 + lane] = acc[mt][nt][i];
+  __syncthreads();
+  // ---- reduce the four partial sums, bias + ReLU, channels-last bf16 rows of 32 (16 real channels + 16 zeros) ----
+  __nv_bfloat16* orow = out + ((size_t)(b * groups + g_idx) * 1024 + (size_t)oh * 32) * 32;
+  for (int o = tid; o < 32 * 8; o += 128) {         // one item = channel pair (2 * cp, 2 * cp + 1) of one position
+    const int ow = o >> 3, cp = o & 7;
+    // fragment coordinates of (position ow, channels 2cp, 2cp+1): mt = ow / 16, row r = ow % 16 -> g = r % 8, upper = r / 8;
+    // nt = cp / 4, tig = cp % 4 -> accumulator elements i = 2 * upper, 2 * upper + 1 of lane g * 4 + tig
+    const int mt = ow >> 4, r = ow & 15, gg = r & 7, upper = r >> 3, nt = cp >> 2, tg = cp & 3;
+    const int ln = gg * 4 + tg, e0 = (mt * 2 + nt) * 4 + 2 * upper;
+    float s0 = bias[2 * cp], s1 = bias[2 * cp + 1];
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      s0 += part[(w * 16 + e0) * 32 + ln];
+      s1 += part[(w * 16 + e0 + 1) * 32 + ln];
+    }
+    *reinterpret_cast<__nv_bfloat162*>(orow + ow * 32 + 2 * cp) = __floats2bfloat162_rn(fmaxf(s0, 0.0f), fmaxf(s1, 0.0f));
+  }
+  for (int o = tid; o < 32 * 2; o += 128)           // channels 16..31 = 0
+    *reinterpret_cast<uint4*>(orow + (o >> 1) * 32 + 16 + (o & 1) * 8) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // Layers 2-4: Conv3d(C -> *, kernel 3x3x3, stride (st, 2, 2), padding 1) over a channels-last activation [B][Ti][Hi][Wi][C]

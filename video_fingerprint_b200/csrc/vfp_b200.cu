@@ -1123,6 +1123,7 @@ struct vfp3d_weights {
   int kp[4] = {0, 0, 0, 0};            // padded K of the four conv GEMMs
   __nv_bfloat16* w[4] = {nullptr, nullptr, nullptr, nullptr};   // [Np][Kp] K-major, BN folded
   float* b[4] = {nullptr, nullptr, nullptr, nullptr};           // [Np]
+  uint2* l1_pack = nullptr;   // layer 1 as mma.sync B fragments (conv3d_l1_kernel)
   CUtensorMap tm[4];
   float *tc_w = nullptr, *tc_b = nullptr, *ta_w = nullptr, *ta_b = nullptr, *p0_w = nullptr, *p0_b = nullptr, *p3_w = nullptr, *p3_b = nullptr;
   std::vector<void*> allocs;
@@ -1197,6 +1198,19 @@ int vfp3d_weights_create(const vfp_tensor_desc* tensors, int n_tensors, int fram
       bf[co] = cb[co] * bn.scale[co] + bn.shift[co];
     }
     if (upload3d(w, to_bf16(wf), &w->w[l]) || upload3d(w, bf, &w->b[l])) return bail("");
+    if (l == 0) {   // B fragments of mma.sync m16n8k16 per K run of 16: lane (g, tig) holds W[n = nt*8 + g][k0 + 2tig, +1] and [.. + 8, + 9]
+      const int n_runs = kt * 5;
+      std::vector<uint2> pack((size_t)n_runs * 2 * 32);
+      auto bf16bits = [](float x) { __nv_bfloat16 h = __float2bfloat16(x); uint16_t u; memcpy(&u, &h, 2); return (uint32_t)u; };
+      for (int run = 0; run < n_runs; ++run)
+        for (int nt = 0; nt < 2; ++nt)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, tig = lane & 3, co = nt * 8 + g;
+            const float* row = wf.data() + (size_t)co * w->kp[0] + (size_t)run * 16 + 2 * tig;
+            pack[((size_t)run * 2 + nt) * 32 + lane] = make_uint2(bf16bits(row[0]) | (bf16bits(row[1]) << 16), bf16bits(row[8]) | (bf16bits(row[9]) << 16));
+          }
+      if (upload3d(w, pack, &w->l1_pack)) return bail("");
+    }
     if (make_tmap_rows_bf16(&w->tm[l], w->w[l], (uint64_t)k3dNp[l], (uint64_t)w->kp[l], (uint64_t)w->kp[l], (uint32_t)std::min(k3dNp[l], 256), 64))
       return bail("tensor map encode failed");
   }
@@ -1223,7 +1237,7 @@ size_t vfp3d_forward_workspace_bytes(const vfp3d_weights* w, int64_t clips_per_p
   const Dims3d d = dims3d(clips_per_pass, n_frames, w->fs);
   size_t a = 0, act = 0;
   for (int l = 0; l < 4; ++l) {
-    a = std::max(a, align_up((size_t)d.m[l] * w->kp[l] * 2, 1024));
+    if (l > 0) a = std::max(a, align_up((size_t)d.m[l] * w->kp[l] * 2, 1024));   // layer 1 needs no im2col matrix
     act += align_up((size_t)d.m[l] * k3dNp[l] * 2, 1024);
   }
   return a + act + 1024;
@@ -1247,7 +1261,7 @@ int vfp3d_forward(const vfp3d_weights* w, const void* frames, int frame_dtype, i
     const Dims3d d = dims3d(B, n_frames, w->fs);
     uint8_t* ws = static_cast<uint8_t*>(workspace);
     size_t a_bytes = 0;
-    for (int l = 0; l < 4; ++l) a_bytes = std::max(a_bytes, align_up((size_t)d.m[l] * w->kp[l] * 2, 1024));
+    for (int l = 1; l < 4; ++l) a_bytes = std::max(a_bytes, align_up((size_t)d.m[l] * w->kp[l] * 2, 1024));
     __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* act[4];
     size_t off = a_bytes;
@@ -1256,14 +1270,15 @@ int vfp3d_forward(const vfp3d_weights* w, const void* frames, int frame_dtype, i
     for (int l = 0; l < 4; ++l) {
       const long long items = d.m[l] * (w->kp[l] / 8);
       const unsigned grid = (unsigned)std::min<long long>((items + 255) / 256, (long long)device_sm_count() * 32);
-      if (l == 0) {
-        const size_t smem = (size_t)w->fs * 5 * 204 * 2 + 16;
+      if (l == 0) {   // layer 1 straight from the frames on the register-fragment tensor path, no im2col matrix
+        const size_t smem = (((size_t)w->fs * 5 * 204 * 2 + 4 + 15) & ~size_t(15)) + 4 * 16 * 32 * 4;
         static bool configured = false;
         if (!configured) {
-          VFP_CUDA(cudaFuncSetAttribute(im2col3d_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 5 * 204 * 2 + 16));
+          VFP_CUDA(cudaFuncSetAttribute(conv3d_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 5 * 204 * 2 + 32 + 4 * 16 * 32 * 4));
           configured = true;
         }
-        im2col3d_frames_kernel<<<(unsigned)(B * d.G * 32), 256, smem, st>>>(fr, frame_dtype, n_frames, w->fs, d.G, w->kp[0], A);
+        conv3d_l1_kernel<<<(unsigned)(B * d.G * 32), 128, smem, st>>>(fr, frame_dtype, n_frames, w->fs, d.G, w->l1_pack, w->b[0], act[0]);
+        continue;
       } else {
         const int Ti = l == 3 ? d.T3 : d.G, Hi = 64 >> l, st_t = l == 2 ? 2 : 1, To = l == 1 ? d.G : d.T3;
         im2col3d_ndhwc_kernel<<<grid, 256, 0, st>>>(act[l - 1], (int)B, Ti, Hi, Hi, k3dCinPad[l], st_t, To, Hi / 2, Hi / 2, w->kp[l], A);

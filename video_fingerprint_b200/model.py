@@ -254,7 +254,7 @@ class VideoFingerprint3D(nn.Module):
         self.projector = nn.Sequential(nn.Linear(128, 128), nn.ReLU(inplace=True), nn.Dropout(dropout), nn.Linear(128, embedding_dim))
         self.temperature = nn.Parameter(torch.ones(1) * 0.07)
         self._initialize_weights()
-        self.clips_per_pass = 64     # workspace: the explicit im2col of layer 1 is ~2.4 KB per output position
+        self.clips_per_pass = 1024   # workspace: ~0.6 MB per 64-frame clip (layer-2 im2col + activations)
         self._native_weights: Optional[int] = None
         self._native_key: Optional[tuple] = None
         self._workspace: Optional[torch.Tensor] = None
