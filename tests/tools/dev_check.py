@@ -1,7 +1,7 @@
 """Developer check on a GPU box: forward + join parity against the oracle / golden files."""
 import os, sys, time, json
 import numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle.weights import make_state_dict, make_clips
 from oracle.forward_oracle import forward_oracle, fingerprint_clips

@@ -4,7 +4,7 @@
   cfg4  all-pairs threshold join over N x 256 unit vectors with planted duplicates (N = 1M by default)
   cfg5  top-10 inner-product search, DB 10M x 256 vs 100k queries
 
-Prints one JSON line per config. Run on the GPU box: python scripts/run_configs.py [--small]"""
+Prints one JSON line per config. Run on the GPU box: python tests/tools/run_configs.py [--small]"""
 import argparse
 import json
 import os
@@ -14,7 +14,7 @@ import time
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import video_fingerprint_b200 as vfp  # noqa: E402
 from oracle.forward_oracle import fingerprint_clips  # noqa: E402
