@@ -138,6 +138,22 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
   }
 }
 
+// Wait for roles that are far from the critical path (frame copy issuer, transposers): sleeping between polls keeps their
+// retries out of the issue slots and the shared-memory port the critical roles need.
+__device__ __forceinline__ void mbar_wait_lazy(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(100);
+    if (++spins > 40000000u) {   // several seconds
+      atomicExch(&g_vfp_device_error, (unsigned int)kErrMbarTimeout);
+      if (*reinterpret_cast<volatile int*>(&g_vfp_hang_mode)) return;
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // TMA tiled loads (global -> shared), completion on an mbarrier
 // ------------------------------------------------------------------------------------------

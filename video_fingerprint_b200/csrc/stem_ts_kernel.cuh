@@ -222,13 +222,13 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
     for (int li = 0; li < n_local; ++li) {
       const int t = li & 1;
       uint8_t* tile = tilebuf + t * kStemTileBytes;
-      mbar_wait_relaxed(&tile_empty[t], (uint32_t)(((li >> 1) & 1) ^ 1));
+      mbar_wait_lazy(&tile_empty[t], (uint32_t)(((li >> 1) & 1) ^ 1));
       const uint8_t* pl[3];
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const uint32_t n = n0 + c;
         const int s = (slot0 + c) % kTsRawSlots;
-        mbar_wait_relaxed(&raw_full[s], (n / kTsRawSlots) & 1u);
+        mbar_wait_lazy(&raw_full[s], (n / kTsRawSlots) & 1u);
         pl[c] = rawbuf + s * kStemRawSlotBytes;
       }
       if (!(kTsKnock & 2)) stem_transpose_frame(pl, tile, p.frame_dtype, ltid, kTsXposeWarps * 32);
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
           // frame after next into L2 now and the copy only pays the L2 latency
           if (li + 2 < n_local && !(kTsKnock & 4)) bulk_prefetch_l2(src + 2 * (size_t)gridDim.x * frame_bytes, 3 * plane_bytes);
           for (int c = 0; c < 3; ++c) {
-            mbar_wait_relaxed(&raw_empty[slot], ph ^ 1);
+            mbar_wait_lazy(&raw_empty[slot], ph ^ 1);
             if (kTsKnock & 4) {
               mbar_arrive(&raw_full[slot]);
             } else {
