@@ -395,10 +395,10 @@ def run_ours(args):
     gbs = STAGE_BYTES.get(dom, 0) * n_clips / (dom_ms / 1000.0) / 1e9
     frac_t, frac_h = tflops / peaks["tc_sustained"], gbs / peaks["hbm"]
     hbm_bound = frac_h > frac_t  # the binding roofline is the one the kernel sits closer to
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r01_v5_stem_ts_full.txt:
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r01_v6_stem_ts_full.txt:
     # dram__bytes_read.sum + dram__bytes_write.sum of one stem launch over a 16 384-frame conv pass); below the algorithmic
     # 939.5 MB because the tail of the output is still in L2 when the kernel ends
-    ncu_traffic = {"stem_fused": 402.772480e6 + 491.417344e6}
+    ncu_traffic = {"stem_fused": 402.787584e6 + 488.215040e6}
     roofline = {
         "bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
         "achieved": gbs if hbm_bound else tflops, "peak": peaks["hbm"] if hbm_bound else peaks["tc_sustained"],
