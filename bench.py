@@ -383,6 +383,44 @@ def run_ours(args):
         }
         del E_local
 
+    # ---- the neighbouring steps of SURVEY.md section 8(f), timed briefly (rank 0, device-resident inputs, CUDA events) ----
+    extras = None
+    if not args.no_extras and rank == 0:
+        extras = {}
+
+        def timed(fn, reps=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        try:
+            dec = torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, device=dev)   # one video's decoded 1080p frames
+            ms_pre = timed(lambda: vfp.preprocess_frames_device(dec))
+            extras["preprocess_1080p"] = {"frames_per_s": 64 / ms_pre * 1e3, "ms_per_64_frames": ms_pre, "hbm_gbs": 64 * 1088 * 1080 * 3 / ms_pre / 1e6,
+                                          "what": "INTER_AREA resize to a short side of 64 + centre crop (fingerprint.py:186-214), bit-exact with cv2"}
+            del dec
+            g3 = torch.Generator(device=dev).manual_seed(5)
+            nm = 8192
+            Em = torch.randn((nm, 256), generator=g3, device=dev)
+            Em = Em / Em.norm(dim=1, keepdim=True)
+            ids = np.repeat(np.arange(nm // 2), 2)
+            ms_met = timed(lambda: (vfp.compute_retrieval_metrics(Em, ids), vfp.compute_discrimination_metrics(Em, ids)), reps=2)
+            extras["trainer_metrics"] = {"embeddings": nm, "ms_both_functions": ms_met, "what": "R@k, mAP, P/R/F1/FPR, AUC-ROC (train.py:285-358, 439-481), host bookkeeping included"}
+            m3 = vfp.create_model("3d").eval()
+            n3 = min(2048, n_clips)
+            x3 = frames[: n3 * T_FRAMES].view(n3, T_FRAMES, 3, 64, 64)
+            ms_3d = timed(lambda: m3(x3))
+            extras["model_3d"] = {"videos_per_s": n3 / ms_3d * 1e3, "clips": n3, "frames": T_FRAMES, "frame_stride": 16, "what": "VideoFingerprint3D forward (model.py:406-512), bf16 frames in HBM"}
+            del m3
+        except Exception as exc:  # these are side measurements: never fail the headline line
+            extras["error"] = repr(exc)
+
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----
@@ -425,7 +463,7 @@ def run_ours(args):
             "frames_per_pass": args.frames_per_pass, "l2": f"inputs ({n_clips * T_FRAMES * 24576 / 1e9:.1f} GB) and per-pass activations exceed the 126 MB L2; no flush needed",
             "parallelism": f"clips sharded over {world} GPU(s), no data-path collective",
         },
-        "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "stage_ms_per_step": stages, "join": join, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "stage_ms_per_step": stages, "join": join, "extras": extras, "clocks": clocks,
     }
     if not args.no_cpu and world == 1:
         r, n, dt = cpu_reference_rate(args.cpu_seconds, 2048)
@@ -454,6 +492,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-join", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the brief preprocess / trainer-metrics / 3-D model timings")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -32,29 +32,49 @@ struct PreprocessParams {
 };
 
 constexpr int kPreMaxSpan = 8192;   // bytes of one staged source row segment (sx_count * 3 <= 8192: scale factors up to ~42)
+constexpr int kPreRowsPerStage = 8; // source rows staged per barrier pair: their loads are all in flight together
 
 __global__ void __launch_bounds__(192) preprocess_area_kernel(const PreprocessParams p) {
-  __shared__ uint8_t row[kPreMaxSpan];
+  extern __shared__ __align__(16) uint8_t pre_rows[];   // kPreRowsPerStage slots of `pitch` bytes
   const int dy = blockIdx.x, f = blockIdx.y;
   const int dx = threadIdx.x / 3, c = threadIdx.x - 3 * dx;
   const int xb = p.x_begin[dx], xe = p.x_begin[dx + 1];
   const int yb = p.y_begin[dy], ye = p.y_begin[dy + 1];
   const uint8_t* frame = p.src + (size_t)f * p.H * p.W * 3;
   const int span = p.sx_count * 3;
+  const int pitch = (span + 32 + 15) & ~15;
   float sum = 0.0f;
   int isum = 0;
-  for (int j = yb; j < ye; ++j) {
-    const uint8_t* srow = frame + ((size_t)p.y_si[j] * p.W + p.sx_min) * 3;
+  for (int j0 = yb; j0 < ye; j0 += kPreRowsPerStage) {
+    const int nr = min(kPreRowsPerStage, ye - j0);
     __syncthreads();
-    for (int i = threadIdx.x; i < span; i += 192) row[i] = srow[i];
+    // coalesced copy of the row segments: 16-byte vectors between the first and last aligned address, single bytes at the two
+    // ends; logical byte i of a segment is staged at slot[off + i] with off = 16 - head, which keeps the vector stores aligned
+    for (int r = 0; r < nr; ++r) {
+      const uint8_t* srow = frame + ((size_t)p.y_si[j0 + r] * p.W + p.sx_min) * 3;
+      uint8_t* slot = pre_rows + r * pitch;
+      const int head = (int)((16 - (reinterpret_cast<uintptr_t>(srow) & 15)) & 15);
+      const int off = 16 - head;
+      const int nvec = span > head ? (span - head) >> 4 : 0;
+      const int tail0 = head + 16 * nvec;
+      for (int i = threadIdx.x; i < head && i < span; i += 192) slot[off + i] = srow[i];
+      const uint4* v = reinterpret_cast<const uint4*>(srow + head);
+      for (int i = threadIdx.x; i < nvec; i += 192) *reinterpret_cast<uint4*>(slot + 16 + 16 * i) = __ldg(v + i);
+      for (int i = tail0 + threadIdx.x; i < span; i += 192) slot[off + i] = srow[i];
+    }
     __syncthreads();
-    if (p.mode == 0) {
-      float buf = 0.0f;
-      for (int k = xb; k < xe; ++k) buf = __fadd_rn(buf, __fmul_rn((float)row[(p.x_si[k] - p.sx_min) * 3 + c], p.x_alpha[k]));
-      const float t = __fmul_rn(p.y_beta[j], buf);
-      sum = (j == yb) ? t : __fadd_rn(sum, t);
-    } else {
-      for (int k = xb; k < xe; ++k) isum += row[(p.x_si[k] - p.sx_min) * 3 + c];
+    for (int r = 0; r < nr; ++r) {
+      const int j = j0 + r;
+      const uint8_t* srow = frame + ((size_t)p.y_si[j] * p.W + p.sx_min) * 3;
+      const uint8_t* rowv = pre_rows + r * pitch + 16 - (int)((16 - (reinterpret_cast<uintptr_t>(srow) & 15)) & 15);
+      if (p.mode == 0) {
+        float buf = 0.0f;
+        for (int k = xb; k < xe; ++k) buf = __fadd_rn(buf, __fmul_rn((float)rowv[(p.x_si[k] - p.sx_min) * 3 + c], p.x_alpha[k]));
+        const float t = __fmul_rn(p.y_beta[j], buf);
+        sum = (j == yb) ? t : __fadd_rn(sum, t);
+      } else {
+        for (int k = xb; k < xe; ++k) isum += rowv[(p.x_si[k] - p.sx_min) * 3 + c];
+      }
     }
   }
   float v;

@@ -1108,7 +1108,13 @@ int vfp_preprocess_frames(const uint8_t* frames_hwc, int n_frames, int height, i
   p.inv_area = (float)(1.0 / (isx * isy));
   p.x_begin = dev + o_xb; p.x_si = dev + o_xs; p.x_alpha = reinterpret_cast<const float*>(dev + o_xa);
   p.y_begin = dev + o_yb; p.y_si = dev + o_ys; p.y_beta = reinterpret_cast<const float*>(dev + o_ya);
-  preprocess_area_kernel<<<dim3(64, (unsigned)n_frames), 192, 0, st>>>(p);
+  const size_t pre_smem = (size_t)kPreRowsPerStage * ((p.sx_count * 3 + 32 + 15) & ~15);
+  static bool pre_configured = false;
+  if (!pre_configured) {
+    VFP_CUDA(cudaFuncSetAttribute(preprocess_area_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreRowsPerStage * (kPreMaxSpan + 48)));
+    pre_configured = true;
+  }
+  preprocess_area_kernel<<<dim3(64, (unsigned)n_frames), 192, pre_smem, st>>>(p);
   VFP_CUDA(cudaGetLastError());
   return 0;
 }
