@@ -1,20 +1,89 @@
-// Host launch helpers for gemm_tcgen05_kernel.
+// Host launch helpers: per-device kernel configuration, programmatic dependent launch, gemm_tcgen05_kernel grids.
 #pragma once
+#include <atomic>
+#include <mutex>
+#include <unordered_set>
+#include <utility>
+
 #include "epilogues.cuh"
 #include "gemm_sm100.cuh"
 #include "tmap.cuh"
 
 namespace vfp {
 
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs)
 inline int device_sm_count() {
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
+  static std::atomic<int> sms[kMaxDevices];
+  const int dev = current_device();
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (!n) {
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    sms[dev].store(n, std::memory_order_relaxed);
   }
-  return sms;
+  return n;
+}
+
+// Upper bound on the CTAs a persistent kernel launches (vfp_set_tuning key 8; 0 = one per SM). Two pipelines that
+// run side by side on different streams can each be given part of the GPU this way.
+inline std::atomic<int>& persistent_cta_limit() {
+  static std::atomic<int> v{0};
+  return v;
+}
+inline int persistent_grid() {
+  const int lim = persistent_cta_limit().load(std::memory_order_relaxed);
+  const int sms = device_sm_count();
+  return (lim > 0 && lim < sms) ? lim : sms;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel, so "already configured" is
+// remembered per (kernel, device ordinal) - a process-wide flag breaks the second GPU of a process.
+inline cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::unordered_set<unsigned long long> done;
+  const unsigned long long key = (reinterpret_cast<unsigned long long>(kernel) << 6) ^ (unsigned long long)current_device();
+  {
+    std::lock_guard<std::mutex> g(mu);
+    if (done.count(key)) return cudaSuccess;
+  }
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) {
+    std::lock_guard<std::mutex> g(mu);
+    done.insert(key);
+  }
+  return e;
+}
+
+// Programmatic dependent launch (vfp_set_tuning key 7, default on): every kernel of the forward chain executes
+// griddepcontrol.launch_dependents at its top and griddepcontrol.wait before it touches memory, so the next
+// kernel's CTAs are scheduled - and run their prologue (barrier init, TMEM allocation, descriptor prefetch) - while
+// the tail of the current kernel drains. Kernels launched this way MUST call pdl_wait() (sm100_primitives.cuh).
+inline std::atomic<int>& pdl_enabled() {
+  static std::atomic<int> v{1};
+  return v;
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled().load(std::memory_order_relaxed) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, class Epi, int MT = 1, bool SWAP = false>
@@ -24,18 +93,12 @@ inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, con
   constexpr int kSmem = L::kTotal + Epi::kExtraSmemBytes;
   static_assert(kSmem <= 232448, "shared memory budget");
   auto kernel = gemm_tcgen05_kernel<BLOCK_N, BLOCK_K, STAGES, Epi, MT, SWAP>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), kSmem); e != cudaSuccess) return e;
   const int m_super = (shape.m_tiles + MT - 1) / MT;
   const int total = shape.row_resident ? m_super * shape.n_segments : m_super * shape.n_tiles;
   if (total <= 0) return cudaSuccess;
-  const int grid = total < device_sm_count() ? total : device_sm_count();
-  kernel<<<grid, gemm_threads<BLOCK_N, Epi>(), kSmem, stream>>>(ta, tb, shape, ep);
-  return cudaGetLastError();
+  const int grid = total < persistent_grid() ? total : persistent_grid();
+  return launch_kernel(kernel, dim3(grid), dim3(gemm_threads<BLOCK_N, Epi>()), kSmem, stream, ta, tb, shape, ep);
 }
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, int KB, class Epi>
@@ -46,17 +109,11 @@ inline cudaError_t launch_gemm_bres(const CUtensorMap& ta, const CUtensorMap& tb
   static_assert(kSmem <= 232448, "shared memory budget");
   if (shape.k_blocks != KB) return cudaErrorInvalidValue;
   auto kernel = gemm_bres_tcgen05_kernel<BLOCK_N, BLOCK_K, STAGES, KB, Epi>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) return e;
-    configured = true;
-  }
+  if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), kSmem); e != cudaSuccess) return e;
   const long long total = (long long)shape.m_tiles * shape.n_tiles;
   if (total <= 0) return cudaSuccess;
-  const int grid = total < device_sm_count() ? (int)total : device_sm_count();
-  kernel<<<grid, gemm_threads<BLOCK_N, Epi>(), kSmem, stream>>>(ta, tb, shape, ep);
-  return cudaGetLastError();
+  const int grid = total < persistent_grid() ? (int)total : persistent_grid();
+  return launch_kernel(kernel, dim3(grid), dim3(gemm_threads<BLOCK_N, Epi>()), kSmem, stream, ta, tb, shape, ep);
 }
 
 inline GemmShape plain_shape(long long M, int N, int K, int block_n, int block_k, int group_m = 16) {

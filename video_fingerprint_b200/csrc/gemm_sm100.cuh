@@ -150,6 +150,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   // the tile walk runs over super-tiles of MT row tiles
   GemmShape shape = shape_in;
   const int m_tiles_real = shape_in.m_tiles;
@@ -176,6 +177,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; its results are needed from here on
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -365,6 +367,7 @@ gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const long long total = (long long)shape.m_tiles * shape.n_tiles;
   const long long per = (total + gridDim.x - 1) / gridDim.x;
   const long long u0 = (long long)blockIdx.x * per;
@@ -393,6 +396,7 @@ gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail; its results are needed from here on
 
   if (warp == 0) {
     if (lane == 0) {

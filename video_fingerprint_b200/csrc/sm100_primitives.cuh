@@ -27,6 +27,13 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Programmatic dependent launch: launch_dependents lets the next kernel of the stream be scheduled as soon as every CTA of
+// this grid has issued it (or exited); wait blocks until the PREVIOUS grid has completed and its memory is visible.
+// Both are no-ops for a kernel launched without the programmatic-serialization attribute. Every kernel that may be
+// launched with the attribute must execute pdl_wait() before its first access to memory another kernel produced.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Device-visible error word: kernels write a nonzero code and trap instead of spinning forever.
 // (a hung kernel on a shared box costs a strike; a trapped one only costs the call.)
 __device__ unsigned int g_vfp_device_error = 0;

@@ -19,6 +19,8 @@ constexpr int kHeadDim = 32;
 // ---------------------------------------------------------------------------------------------
 __global__ void token_map_kernel(const int* __restrict__ cu, int n_clips, int n_tokens, int* __restrict__ tok_pos,
                                  int* __restrict__ tok_len) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_tokens) return;
   int lo = 0, hi = n_clips;  // find v with cu[v] <= t < cu[v+1]
@@ -41,6 +43,8 @@ __global__ void __launch_bounds__(256)
 add_layernorm_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta /*nullable*/,
                           const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                           int n_tokens) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= n_tokens) return;
@@ -87,6 +91,8 @@ add_layernorm_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict
 __global__ void __launch_bounds__(256)
 add_convert_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta /*nullable*/,
                         __nv_bfloat16* __restrict__ xbf, long long n8) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n8) return;
   float4* xr = reinterpret_cast<float4*>(x) + 2 * i;
@@ -164,6 +170,7 @@ temporal_conv_kernel(const float* __restrict__ x, const int* __restrict__ tok_po
   // ws[bt][g]: bt = 0..2 branch 0 (k=3, centred taps 4..6), 3..7 branch 1 (k=5, taps 3..7), 8..14 branch 2 (k=7,
   // taps 2..8), 15..25 branch 3 (k=11, taps 0..10)
   __shared__ float4 ws[26][64];
+  pdl_launch_dependents();
   for (int idx = threadIdx.x; idx < 26 * 64; idx += 256) {
     const int bt = idx >> 6, gg = idx & 63;
     const int j = bt < 3 ? 0 : bt < 8 ? 1 : bt < 15 ? 2 : 3;
@@ -173,6 +180,7 @@ temporal_conv_kernel(const float* __restrict__ x, const int* __restrict__ tok_po
                              __ldg(w + (2 * 11 + tap) * kDim + o), __ldg(w + (3 * 11 + tap) * kDim + o));
   }
   __syncthreads();
+  pdl_wait();   // the weights above are static; x / tok_pos / tok_len come from the previous kernels
   const int g = threadIdx.x & 63;
   const int t0 = (blockIdx.x * 4 + (threadIdx.x >> 6)) * kTcTok;
   const int t_end = min(t0 + kTcTok, n_tokens);
@@ -233,6 +241,8 @@ __global__ void __launch_bounds__(128)
 attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ cu, __nv_bfloat16* __restrict__ out) {
   __shared__ __align__(16) __nv_bfloat16 Ks[kAttKeys * kAttKPitch];
   __shared__ __align__(16) __nv_bfloat16 Vt[kHeadDim * kAttVPitch];
+  pdl_launch_dependents();
+  pdl_wait();
   const int clip = blockIdx.x, head = blockIdx.y;
   const int t0 = cu[clip];
   const int T = cu[clip + 1] - t0;
@@ -365,6 +375,8 @@ attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restric
 __global__ void __launch_bounds__(256)
 temporal_pool_kernel(const float* __restrict__ x, const float* __restrict__ logits, const int* __restrict__ cu,
                      float* __restrict__ pooled /*[clips][768]*/, __nv_bfloat16* __restrict__ pooled_bf /*same, bf16*/) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int clip = blockIdx.x, c = threadIdx.x;
   const int t0 = cu[clip], T = cu[clip + 1] - t0;
   float sum = 0.f, mx = -INFINITY, m = -INFINITY, l = 0.f, ws = 0.f;
@@ -404,6 +416,8 @@ final_projection_kernel(const float* __restrict__ pooled, const float* __restric
   __shared__ float sp[kClips][3 * kDim];
   __shared__ float sh[kClips][kDim];
   __shared__ float red[kClips][8];
+  pdl_launch_dependents();
+  pdl_wait();
   const int c0 = blockIdx.x * kClips;
   const int tid = threadIdx.x;
   for (int i = tid; i < kClips * 3 * kDim; i += 256) {

@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -303,7 +304,23 @@ size_t forward_ws_total(int64_t F, int64_t C) {
   return token_ws_layout(F, C).total + conv_ws_layout(std::min<int64_t>(F, kConvPassFrames)).total;
 }
 
-constexpr int kMaxClipFrames = 1024;
+// Pipelines of vfp_forward (vfp_set_tuning key 9): token passes are dealt round-robin onto this many internal streams.
+constexpr int kMaxPipes = 4;
+int g_forward_pipes = 2;
+
+// Internal non-blocking streams, created once per device and shared by all calls (work of different calls on the same
+// pipeline stream simply queues up; the fork / join events are per call).
+int pipe_streams(int n, cudaStream_t* out) {
+  static std::mutex mu;
+  static cudaStream_t pool[kMaxDevices][kMaxPipes] = {};
+  std::lock_guard<std::mutex> g(mu);
+  const int dev = current_device();
+  for (int i = 0; i < n; ++i) {
+    if (!pool[dev][i]) VFP_CUDA(cudaStreamCreateWithFlags(&pool[dev][i], cudaStreamNonBlocking));
+    out[i] = pool[dev][i];
+  }
+  return 0;
+}
 
 }  // namespace
 
@@ -330,6 +347,9 @@ int vfp_set_tuning(int key, long long value) {
   if (key == 5 && value >= 0 && value <= 4096) { g_join_prefetch = (int)value; return 0; }
   if (key == 6 && value >= 0 && value <= 4096) { g_topk_prefetch = (int)value; return 0; }
   if (key == 3 && value >= 64 && value <= kConvPassFrames) { g_conv_pass_frames = value; return 0; }
+  if (key == 7 && value >= 0 && value <= 1) { pdl_enabled().store((int)value); return 0; }            // programmatic dependent launch
+  if (key == 8 && value >= 0 && value <= 4096) { persistent_cta_limit().store((int)value); return 0; }  // CTAs per persistent kernel (0 = all SMs)
+  if (key == 9 && value >= 1 && value <= kMaxPipes) { g_forward_pipes = (int)value; return 0; }        // pipelines (internal streams) of vfp_forward
   if (key == 2) {  // hang diagnosis: timed-out mbarrier waits are logged and abandoned instead of trapping
     const int mode = value != 0;
     const unsigned int zero = 0;
@@ -638,14 +658,10 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     if (make_tmap_out(&sp.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (stem out)");
     sp.frames = frames; sp.frame_dtype = frame_dtype; sp.n_frames = F;
     sp.c2_bias = w->c2_b;
-    static bool configured = false;
-    if (!configured) {
-      VFP_CUDA(cudaFuncSetAttribute(stem_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemTsSmem::kTotal));
-      configured = true;
-    }
+    VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(stem_ts_kernel), StemTsSmem::kTotal));
     g_prof.launches += 1;
-    const int grid = (int)std::min<int64_t>(F, device_sm_count());
-    stem_ts_kernel<<<grid, kStemThreads, StemTsSmem::kTotal, st>>>(sp);
+    const int grid = (int)std::min<int64_t>(F, persistent_grid());
+    VFP_CUDA(launch_kernel(stem_ts_kernel, dim3(grid), dim3(kStemThreads), StemTsSmem::kTotal, st, sp));
     g_prof.mark(kStStemFused, st);
   } else if (fused) {
     StemParams sp{};
@@ -653,11 +669,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     if (make_tmap_out(&sp.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (stem out)");
     sp.frames = frames; sp.frame_dtype = frame_dtype; sp.n_frames = F;
     sp.c1_wpack = w->c1_wpack_perm; sp.c1_bias = w->c1_bias; sp.c2_bias = w->c2_b;
-    static bool configured = false;
-    if (!configured) {
-      VFP_CUDA(cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemSmem::kTotal));
-      configured = true;
-    }
+    VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(stem_fused_kernel), StemSmem::kTotal));
     g_prof.launches += 1;
     const int grid = (int)std::min<int64_t>(F, device_sm_count());
     stem_fused_kernel<<<grid, kStemThreads, StemSmem::kTotal, st>>>(sp);
@@ -755,7 +767,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   g_prof.launches += 8 + 7 * (unsigned long long)w->n_attn;
   VFP_CUDA(cudaMemcpyAsync(d_cu, cu_rel.data(), (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, st));
   // cu_rel is pageable: the copy is staged before the call returns, so the vector may die with this scope.
-  token_map_kernel<<<(unsigned)((F + 255) / 256), 256, 0, st>>>(d_cu, C, (int)F, tok_pos, tok_len);
+  VFP_CUDA(launch_kernel(token_map_kernel, dim3((unsigned)((F + 255) / 256)), dim3(256), 0, st, d_cu, C, (int)F, tok_pos, tok_len));
   g_prof.mark(kStMisc, st);
 
   // ---- frame encoder, one conv pass at a time (frames are independent: slices ignore clip boundaries) ----
@@ -801,8 +813,8 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   // ---- multi-scale temporal convolutions (residual) ----
   {
     const unsigned grid = (unsigned)((F + 4 * kTcTok - 1) / (4 * kTcTok));
-    temporal_conv_kernel<<<grid, 256, 0, st>>>(xa, tok_pos, tok_len, w->tc_w[0], w->tc_b[0], xb, (int)F);
-    temporal_conv_kernel<<<grid, 256, 0, st>>>(xb, tok_pos, tok_len, w->tc_w[1], w->tc_b[1], xa, (int)F);
+    VFP_CUDA(launch_kernel(temporal_conv_kernel, dim3(grid), dim3(256), 0, st, xa, tok_pos, tok_len, w->tc_w[0], w->tc_b[0], xb, (int)F));
+    VFP_CUDA(launch_kernel(temporal_conv_kernel, dim3(grid), dim3(256), 0, st, xb, tok_pos, tok_len, w->tc_w[1], w->tc_b[1], xa, (int)F));
     g_prof.mark(kStTemporalConv, st);
   }
   // ---- attention blocks ----
@@ -811,15 +823,15 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   // residual updates travel as bf16 `delta` and are folded into the fp32 stream by the next LayerNorm (see there)
   for (int b = 0; b < w->n_attn; ++b) {
     const AttnBlockWeights& a = w->attn[b];
-    add_layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, b > 0 ? delta : nullptr, a.ln1_w, a.ln1_b, xn, (int)F);
+    VFP_CUDA(launch_kernel(add_layernorm_bf16_kernel, dim3(ln_grid), dim3(256), 0, st, xa, b > 0 ? delta : nullptr, a.ln1_w, a.ln1_b, xn, (int)F));
     g_prof.mark(kStLayerNorm, st);
     if (token_gemm_bf16(xn, F, kDim, a.tm_qkv, 3 * kDim, a.bqkv, 0, qkv)) return 1;
     g_prof.mark(kStQkv, st);
-    attention_mma_kernel<<<att_grid, 128, 0, st>>>(qkv, d_cu, att);
+    VFP_CUDA(launch_kernel(attention_mma_kernel, att_grid, dim3(128), 0, st, qkv, d_cu, att));
     g_prof.mark(kStAttention, st);
     if (token_gemm_bf16(att, F, kDim, a.tm_o, kDim, a.bo, 0, delta)) return 1;
     g_prof.mark(kStOutProj, st);
-    add_layernorm_bf16_kernel<<<ln_grid, 256, 0, st>>>(xa, delta, a.ln2_w, a.ln2_b, xn, (int)F);
+    VFP_CUDA(launch_kernel(add_layernorm_bf16_kernel, dim3(ln_grid), dim3(256), 0, st, xa, delta, a.ln2_w, a.ln2_b, xn, (int)F));
     g_prof.mark(kStLayerNorm, st);
     if (token_gemm_bf16(xn, F, kDim, a.tm_w1, 4 * kDim, a.b1, 2, hbuf)) return 1;
     g_prof.mark(kStMlp1, st);
@@ -827,7 +839,8 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     g_prof.mark(kStMlp2, st);
   }
   // close the last block's residual and make the bf16 copy the pooling GEMM reads
-  add_convert_bf16_kernel<<<(unsigned)((F * kDim / 8 + 255) / 256), 256, 0, st>>>(xa, w->n_attn > 0 ? delta : nullptr, xbf, F * kDim / 8);
+  VFP_CUDA(launch_kernel(add_convert_bf16_kernel, dim3((unsigned)((F * kDim / 8 + 255) / 256)), dim3(256), 0, st, xa, w->n_attn > 0 ? delta : nullptr, xbf,
+                         (long long)(F * kDim / 8)));
   if (features_out)
     VFP_CUDA(cudaMemcpyAsync(features_out + (size_t)f0 * kDim, xa, (size_t)F * kDim * 4, cudaMemcpyDeviceToDevice, st));
   // ---- pooling + head ----
@@ -842,7 +855,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     VFP_CUDA((launch_gemm<256, 64, 3, EpiBiasActTma<false>>(tma, w->tm_pool, s, ep, st)));
     g_prof.mark(kStPoolGemm, st);
   }
-  temporal_pool_kernel<<<(unsigned)C, 256, 0, st>>>(xa, logits, d_cu, pooled, pooled_bf);
+  VFP_CUDA(launch_kernel(temporal_pool_kernel, dim3((unsigned)C), dim3(256), 0, st, xa, logits, d_cu, pooled, pooled_bf));
   g_prof.mark(kStPool, st);
   float* emb_dst = emb_out + (size_t)c0 * w->embedding_dim;
   if (w->head_on_tensor_cores) {
@@ -857,8 +870,8 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     en.bias = w->b3; en.out_f32 = emb_dst; en.M = C; en.N = w->embedding_dim;
     VFP_CUDA((launch_gemm<256, 64, 4, EpiBiasL2Norm>(tma, w->tm_head3, s, en, st)));
   } else {
-    final_projection_kernel<8><<<(unsigned)((C + 7) / 8), 256, 0, st>>>(pooled, w->w0t, w->b0, w->w3t, w->b3, w->embedding_dim,
-                                                                     C, emb_dst);
+    VFP_CUDA(launch_kernel(final_projection_kernel<8>, dim3((unsigned)((C + 7) / 8)), dim3(256), 0, st, pooled, w->w0t, w->b0, w->w3t, w->b3,
+                           w->embedding_dim, C, emb_dst));
   }
   g_prof.mark(kStFinal, st);
   if (g_prof.marks.size() > 4096) g_prof.drain();
@@ -881,32 +894,68 @@ int vfp_forward(const vfp_weights* w, const void* frames, int frame_dtype, const
   for (int i = 0; i < n_clips; ++i) {
     const int T = cu[i + 1] - cu[i];
     if (T <= 0) return fail("vfp_forward: clip " + std::to_string(i) + " has no frames");
-    if (T > kMaxClipFrames || T > w->pe_len)
-      return fail("vfp_forward: clip " + std::to_string(i) + " has " + std::to_string(T) + " frames; limit is " +
-                  std::to_string(std::min(kMaxClipFrames, w->pe_len)));
+    if (T > w->pe_len)   // the positional table of the checkpoint (model.py:77: max_len 10000) is the only length limit
+      return fail("vfp_forward: clip " + std::to_string(i) + " has " + std::to_string(T) + " frames; the positional table holds " +
+                  std::to_string(w->pe_len));
     max_T = std::max(max_T, T);
   }
-  // largest pass (in frames) the workspace can hold; a pass never has more clips than frames
-  int64_t lo = 0, hi = cu[n_clips];
-  while (lo < hi) {
-    const int64_t mid = (lo + hi + 1) / 2;
-    if (forward_ws_total(mid, std::min<int64_t>(mid, n_clips)) <= workspace_bytes) lo = mid; else hi = mid - 1;
-  }
-  const int64_t pass_frames = lo;
+  const int64_t total = cu[n_clips];
+  // The workspace is cut into equal slices, one per pipeline; a pipeline = an internal stream that takes every
+  // n_pipes-th token pass. Passes are independent (disjoint clips, own workspace slice), so the tail of one pass's
+  // kernels overlaps the head of another's, and HBM-bound stages of one pass run beside tensor-bound stages of another.
+  auto fit = [&](size_t bytes) {   // largest pass (in frames) `bytes` can hold; a pass never has more clips than frames
+    int64_t lo = 0, hi = total;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi + 1) / 2;
+      if (forward_ws_total(mid, std::min<int64_t>(mid, n_clips)) <= bytes) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+  };
+  int n_pipes = g_prof.enabled ? 1 : std::max(1, std::min(g_forward_pipes, kMaxPipes));   // stage timing needs one stream
+  n_pipes = (int)std::min<int64_t>(n_pipes, std::max<int64_t>(1, total / kConvPassFrames));  // small calls: one pass on the caller's stream
+  auto slice_bytes = [&](int n) { return workspace_bytes / n / 1024 * 1024; };
+  while (n_pipes > 1 && fit(slice_bytes(n_pipes)) < max_T) --n_pipes;
+  const int64_t pass_frames = fit(slice_bytes(n_pipes));
   if (pass_frames < max_T)
     return fail("vfp_forward: workspace of " + std::to_string(workspace_bytes) + " bytes cannot hold the longest clip (" +
                 std::to_string(max_T) + " frames need " + std::to_string(forward_ws_total(max_T, 1)) + ")");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  int c0 = 0;
-  while (c0 < n_clips) {
-    int c1 = c0;
-    while (c1 < n_clips && (int64_t)cu[c1 + 1] - cu[c0] <= pass_frames) ++c1;
-    if (int rc = forward_pass(w, static_cast<const uint8_t*>(frames), frame_dtype, frame_bytes, cu, c0, c1, emb_out,
-                              features_out, static_cast<uint8_t*>(workspace), st))
-      return rc;
-    c0 = c1;
+  const size_t slice = slice_bytes(n_pipes);
+  // passes of about equal size, a multiple of n_pipes of them
+  int64_t n_pass = (total + pass_frames - 1) / pass_frames;
+  n_pass = (n_pass + n_pipes - 1) / n_pipes * n_pipes;
+  const int64_t target = (total + n_pass - 1) / n_pass;
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  cudaStream_t pipe[kMaxPipes] = {caller, nullptr, nullptr, nullptr};
+  cudaEvent_t fork = nullptr;
+  if (n_pipes > 1) {
+    if (int rc = pipe_streams(n_pipes, pipe)) return rc;
+    VFP_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+    VFP_CUDA(cudaEventRecord(fork, caller));
+    for (int p = 0; p < n_pipes; ++p) VFP_CUDA(cudaStreamWaitEvent(pipe[p], fork, 0));
   }
-  return 0;
+  int rc = 0;
+  int c0 = 0, pass = 0;
+  while (c0 < n_clips && rc == 0) {
+    int c1 = c0 + 1;   // a clip always fits (pass_frames >= max_T); add clips up to the target, never past the slice capacity
+    while (c1 < n_clips && (int64_t)cu[c1 + 1] - cu[c0] <= pass_frames && (int64_t)cu[c1] - cu[c0] < target) ++c1;
+    const int p = pass % n_pipes;
+    rc = forward_pass(w, static_cast<const uint8_t*>(frames), frame_dtype, frame_bytes, cu, c0, c1, emb_out, features_out,
+                      static_cast<uint8_t*>(workspace) + (size_t)p * slice, pipe[p]);
+    c0 = c1;
+    ++pass;
+  }
+  if (n_pipes > 1) {   // join: the caller's stream continues when every pipeline has drained (also on the error path)
+    for (int p = 0; p < n_pipes; ++p) {
+      cudaEvent_t done = nullptr;
+      if (cudaEventCreateWithFlags(&done, cudaEventDisableTiming) == cudaSuccess) {
+        cudaEventRecord(done, pipe[p]);
+        cudaStreamWaitEvent(caller, done, 0);
+        cudaEventDestroy(done);   // released by the runtime once the recorded work has completed
+      }
+    }
+    cudaEventDestroy(fork);
+  }
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1109,11 +1158,7 @@ int vfp_preprocess_frames(const uint8_t* frames_hwc, int n_frames, int height, i
   p.x_begin = dev + o_xb; p.x_si = dev + o_xs; p.x_alpha = reinterpret_cast<const float*>(dev + o_xa);
   p.y_begin = dev + o_yb; p.y_si = dev + o_ys; p.y_beta = reinterpret_cast<const float*>(dev + o_ya);
   const size_t pre_smem = (size_t)kPreRowsPerStage * ((p.sx_count * 3 + 32 + 15) & ~15);
-  static bool pre_configured = false;
-  if (!pre_configured) {
-    VFP_CUDA(cudaFuncSetAttribute(preprocess_area_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPreRowsPerStage * (kPreMaxSpan + 48)));
-    pre_configured = true;
-  }
+  VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(preprocess_area_kernel), kPreRowsPerStage * (kPreMaxSpan + 48)));
   preprocess_area_kernel<<<dim3(64, (unsigned)n_frames), 192, pre_smem, st>>>(p);
   VFP_CUDA(cudaGetLastError());
   return 0;
@@ -1278,11 +1323,7 @@ int vfp3d_forward(const vfp3d_weights* w, const void* frames, int frame_dtype, i
       const unsigned grid = (unsigned)std::min<long long>((items + 255) / 256, (long long)device_sm_count() * 32);
       if (l == 0) {   // layer 1 straight from the frames on the register-fragment tensor path, no im2col matrix
         const size_t smem = (((size_t)w->fs * 5 * 204 * 2 + 4 + 15) & ~size_t(15)) + 4 * 16 * 32 * 4;
-        static bool configured = false;
-        if (!configured) {
-          VFP_CUDA(cudaFuncSetAttribute(conv3d_l1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 5 * 204 * 2 + 32 + 4 * 16 * 32 * 4));
-          configured = true;
-        }
+        VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(conv3d_l1_kernel), 64 * 5 * 204 * 2 + 32 + 4 * 16 * 32 * 4));
         conv3d_l1_kernel<<<(unsigned)(B * d.G * 32), 128, smem, st>>>(fr, frame_dtype, n_frames, w->fs, d.G, w->l1_pack, w->b[0], act[0]);
         continue;
       } else {

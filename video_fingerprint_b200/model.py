@@ -102,23 +102,26 @@ class VideoFingerprintAttention(nn.Module):
         )
         self.temperature = nn.Parameter(torch.ones(1) * 0.07)
         self.embedding_dim = embedding_dim
-        self.frames_per_pass = 1 << 20  # frames per token pass (workspace: 8.5 KB/frame + 1.8 GB for the conv pass)
-        self._native_weights: Optional[int] = None
-        self._native_key: Optional[tuple] = None
-        self._workspace: Optional[torch.Tensor] = None
+        # frames per token pass (workspace per pass: 8.5 KB/frame + 1.8 GB for the conv pass) and the number of passes kept in
+        # flight on internal streams of the library (vfp_forward deals the passes round-robin onto `pipelines` streams)
+        self.frames_per_pass = 1 << 17
+        self.pipelines = 2
+        self._native: dict = {}          # device index -> (weights handle, key): one native handle per GPU
+        self._workspaces: dict = {}      # device index -> uint8 tensor
 
     # ------------------------------------------------------------------ native weight handle
     def _weights_key(self) -> tuple:
         return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
 
-    def _release_native(self) -> None:
-        if self._native_weights is not None:
-            try:
-                _native.load().vfp_weights_destroy(C.c_void_p(self._native_weights))
-            except Exception:  # pragma: no cover - interpreter teardown
-                pass
-            self._native_weights = None
-            self._native_key = None
+    def _release_native(self, device_index: Optional[int] = None) -> None:
+        for idx in list(self._native) if device_index is None else [device_index]:
+            handle, _ = self._native.pop(idx, (None, None))
+            if handle is not None:
+                try:
+                    with torch.cuda.device(idx):
+                        _native.load().vfp_weights_destroy(C.c_void_p(handle))
+                except Exception:  # pragma: no cover - interpreter teardown
+                    pass
 
     def __del__(self):  # pragma: no cover
         try:
@@ -126,28 +129,32 @@ class VideoFingerprintAttention(nn.Module):
         except Exception:  # interpreter teardown: torch internals may already be gone
             pass
 
-    def _ensure_native(self) -> int:
-        """(Re)build the folded / packed device weights whenever a parameter or buffer changed."""
+    def _ensure_native(self, device_index: int) -> int:
+        """(Re)build the folded / packed device weights of the CURRENT device whenever a parameter or buffer changed.
+        Handles are per device: the packed weights live in the memory of the GPU they were created on."""
         key = self._weights_key()
-        if self._native_weights is not None and key == self._native_key:
-            return self._native_weights
-        self._release_native()
+        handle, have = self._native.get(device_index, (None, None))
+        if handle is not None and key == have:
+            return handle
+        self._release_native(device_index)
         lib = _native.load()
         host = {k: v.detach().to("cpu").contiguous() for k, v in self.state_dict().items()}
         host = {k: (v.float() if v.is_floating_point() else v) for k, v in host.items()}
         descs = (_native.TensorDesc * len(host))()
         for i, (k, v) in enumerate(host.items()):
             descs[i] = _native.TensorDesc(k.encode(), v.data_ptr(), v.numel())
-        handle = C.c_void_p()
-        _native.check(lib.vfp_weights_create(descs, len(host), C.byref(handle)), "vfp_weights_create")
-        self._native_weights = handle.value
-        self._native_key = key
-        return self._native_weights
+        out = C.c_void_p()
+        _native.check(lib.vfp_weights_create(descs, len(host), C.byref(out)), "vfp_weights_create")
+        self._native[device_index] = (out.value, key)
+        return out.value
 
     def _get_workspace(self, nbytes: int, device) -> torch.Tensor:
-        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != device:
-            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=device)
-        return self._workspace
+        ws = self._workspaces.get(device.index)
+        if ws is None or ws.numel() < nbytes:
+            self._workspaces.pop(device.index, None)
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self._workspaces[device.index] = ws
+        return ws
 
     # ------------------------------------------------------------------ packed (variable-length) entry
     @torch.no_grad()
@@ -178,7 +185,7 @@ class VideoFingerprintAttention(nn.Module):
         dev = frames.device
         lib = _native.load()
         with torch.cuda.device(dev):
-            weights = self._ensure_native()
+            weights = self._ensure_native(dev.index)
             n = len(lengths)
             cu = (C.c_int32 * (n + 1))()
             acc = 0
@@ -187,7 +194,8 @@ class VideoFingerprintAttention(nn.Module):
                 acc += t
             cu[n] = acc
             pass_frames = max(min(total, self.frames_per_pass), max(lengths))
-            ws = self._get_workspace(lib.vfp_forward_workspace_bytes(pass_frames, min(pass_frames, n)), dev)
+            slices = max(1, min(int(self.pipelines), -(-total // pass_frames)))   # one workspace slice per pass in flight
+            ws = self._get_workspace(slices * (lib.vfp_forward_workspace_bytes(pass_frames, min(pass_frames, n)) + 1024), dev)
             emb = torch.empty((n, self.embedding_dim), dtype=torch.float32, device=dev)
             feats = torch.empty((total, 256), dtype=torch.float32, device=dev) if return_features else None
             stream = torch.cuda.current_stream(dev).cuda_stream
@@ -292,7 +300,7 @@ class VideoFingerprint3D(nn.Module):
             pass
 
     def _ensure_native(self) -> int:
-        key = self._weights_key()
+        key = (torch.cuda.current_device(),) + self._weights_key()   # the packed weights belong to one GPU
         if self._native_weights is not None and key == self._native_key:
             return self._native_weights
         self._release_native()
