@@ -3,18 +3,26 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): batched fingerprint forward of 10 000 synthetic clips x 64 frames @ 64x64
-per GPU, bf16 frames resident in HBM, random-init weights of the reference architecture. One "step" = one
-pass of `model.fingerprint_packed` over all clips of the rank. Launched under torchrun for N > 1 (one rank
-per GPU, clips sharded, no data-path collective in the forward => weak scaling).
+Workload of the headline line (BASELINE.json configs[1]): batched fingerprint forward of 10 000 synthetic clips x 64
+frames @ 64x64 per GPU, bf16 frames resident in HBM, random-init weights of the reference architecture. One "step" = one
+pass of `model.fingerprint_packed` over all clips of the rank. Launched under torchrun for N > 1 (one rank per GPU, clips
+sharded, no data-path collective in the forward => weak scaling).
 
-One JSON line on stdout (rank 0): value = whole-job videos/s (device-resident inputs), `e2e` = the same metric
-through the public API with HOST (pinned) uint8 frames, host<->device copies inside the timed region,
-`roofline` for the dominant kernel (per-stage CUDA-event times from the library's stage profiler),
-`cpu_baseline` = the oracle's reference-semantics B=1 loop on the box's host cores, `join` = the all-pairs
-cosine threshold join on synthetic unit vectors with planted duplicates (second half of the BASELINE metric).
-`--impl reference` times the reference algorithm's CPU path (oracle port; the reference itself is not
-installable on the GPU box) on the same config.
+One JSON line on stdout (rank 0):
+  value        whole-job videos/s, device-resident inputs, product defaults (two token passes in flight, PDL)
+  e2e          the same metric through the public API `model.fingerprint_host` with HOST (pinned) uint8 frames,
+               host<->device copies inside the timed region
+  roofline     dominant kernel, from per-stage CUDA-event times taken INSIDE a hot multi-step loop (library stage
+               profiler, single pipeline so that stages do not overlap); sum of stages is printed beside that loop's step time
+  cpu_baseline the oracle's reference-semantics B=1 loop on the box's host cores (N = 1 only)
+  join         all-pairs cosine threshold join, 262 144 rows per GPU (weak scaling; second half of the BASELINE metric)
+  cfg3_varlen  BASELINE configs[2]: 10 000 clips of 16-300 frames (+ a few > 500-frame inputs through subsample()),
+               LPT-sharded over the ranks, uint8 frames in HBM, parity spot-check against the oracle inside the run
+  cfg4_join    BASELINE configs[3]: 1 048 576 rows in total, row-block sharded, NCCL all-gather overlapped with the
+               local block (strong scaling), parity spot-check against an fp32 matmul
+  cfg5_topk    BASELINE configs[4]: top-10 of 100 000 queries (sharded) against 10 000 000 database rows
+`--impl reference` times the reference algorithm's CPU path (oracle port; the reference itself is not installable on the
+GPU box) on the same config.
 """
 from __future__ import annotations
 
@@ -35,8 +43,15 @@ sys.path.insert(0, ROOT)
 
 N_CLIPS = 10_000
 T_FRAMES = 64
-FLOPS_PER_CLIP = 39_806_976 * T_FRAMES + 4096 * T_FRAMES * T_FRAMES + 524_288
+FLOPS_PER_FRAME = 39_806_976
 METRIC = "fingerprint videos/s (64 frames@64^2)"
+
+
+def clip_flops(t: int) -> int:
+    return FLOPS_PER_FRAME * t + 4096 * t * t + 524_288
+
+
+FLOPS_PER_CLIP = clip_flops(T_FRAMES)
 
 # algorithmic FLOPs per clip of each profiled stage (2 FLOP per MAC), T = 64
 _T = T_FRAMES
@@ -46,6 +61,7 @@ STAGE_FLOPS = {
     "stem_fused": 2 * (1024 * 32 * 75 + 256 * 64 * 288) * _T,   # conv1 + conv2 in one kernel
     "conv3_igemm": 2 * 64 * 128 * 576 * _T,
     "conv4_igemm_pool": 2 * 16 * 256 * 1152 * _T,
+    "conv34_fused": 2 * (64 * 128 * 576 + 16 * 256 * 1152) * _T,
     "token_embed_gemm": 2 * (256 * 128 + 128 * 256) * _T,
     "qkv_gemm": 4 * 2 * 256 * 768 * _T,
     "attention": 4 * 4 * _T * _T * 256,
@@ -54,14 +70,13 @@ STAGE_FLOPS = {
     "mlp2_gemm": 4 * 2 * 1024 * 256 * _T,
     "pool_logits_gemm": 2 * 256 * 256 * _T,
 }
-
-
 # algorithmic HBM bytes per clip of the stages whose binding roofline is memory, not the tensor pipe
 STAGE_BYTES = {
-    "conv1_stem": (24576 + 65536) * _T,           # bf16 frame in, bf16 32x32x32 out
-    "conv2_igemm": (65536 + 32768) * _T,          # conv1 output in, 16x16x64 out
+    "conv1_stem": (24576 + 65536) * _T,
+    "conv2_igemm": (65536 + 32768) * _T,
     "stem_fused": (24576 + 32768) * _T,           # bf16 frame in, 16x16x64 out (conv1's output never leaves the SM)
     "conv3_igemm": (32768 + 16384) * _T,
+    "conv34_fused": (32768 + 512) * _T,
     "temporal_conv": 2 * (1024 + 1024) * _T,      # two blocks, fp32 stream in + out
     "layernorm": 8 * (1024 + 512 + 1024 + 512) * _T,
 }
@@ -77,7 +92,7 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms; only the samples that fall INSIDE the timed region
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms; only the samples that fall INSIDE a timed region
     (host timestamps taken around it) are reported. Started before the warm-up so nvidia-smi's start-up is not lost."""
 
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -99,16 +114,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self, t_begin: float, t_end: float):
+    def window(self, t_begin: float, t_end: float):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.06)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        inside = [r for t, r in self.rows if t_begin <= t <= t_end + 0.05 and len(r) >= 6]
+        inside = [r for t, r in list(self.rows) if t_begin <= t <= t_end + 0.05 and len(r) >= 6]
         rows = inside if inside else [r for _, r in self.rows[-3:] if len(r) >= 6]
         sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
@@ -117,8 +126,17 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "samples": len(sm), "samples_inside_timed_region": len(inside)}
 
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
 
-def dist_setup(n_gpus: int):
+
+def dist_setup():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -147,6 +165,28 @@ def max_over_ranks(x: float, world: int, dev) -> float:
     t = torch.tensor([x], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def sum_over_ranks(x: float, world: int, dev) -> float:
+    if world == 1:
+        return x
+    import torch.distributed as dist
+
+    t = torch.tensor([x], dtype=torch.float64, device=dev)
+    dist.all_reduce(t)
+    return float(t.item())
+
+
+def timed_ms(fn, reps: int, world: int, dev) -> float:
+    """CUDA-event time per repetition on the current stream, barrier + synchronize on both sides, max over ranks."""
+    barrier(world)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    barrier(world)
+    return max_over_ranks(a.elapsed_time(b) / reps, world, dev)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -178,10 +218,9 @@ def run_reference(args):
     per_step = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_reference_rate(per_step / 4, 64)
-    rates, clips, secs = [], 0, 0.0
+    clips, secs = 0, 0.0
     for _ in range(args.steps):
-        r, n, dt = cpu_reference_rate(per_step, 512)
-        rates.append(r)
+        _, n, dt = cpu_reference_rate(per_step, 512)
         clips += n
         secs += dt
     value = clips / secs
@@ -198,9 +237,10 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------------
-# our arm
+# synthetic data
 # --------------------------------------------------------------------------------------------------
 def make_join_data(n: int, dev, seed: int = 11):
+    """Unit vectors with planted near-duplicates on both sides of 0.95 (cfg 4)."""
     g = torch.Generator(device=dev).manual_seed(seed)
     E = torch.randn((n, 256), generator=g, device=dev)
     E = E / E.norm(dim=1, keepdim=True)
@@ -213,31 +253,203 @@ def make_join_data(n: int, dev, seed: int = 11):
     return E.contiguous()
 
 
+def make_unit_rows(n: int, dev, seed: int, chunk: int = 1 << 20):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    E = torch.empty((n, 256), dtype=torch.float32, device=dev)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        x = torch.randn((e - s, 256), generator=g, device=dev)
+        E[s:e] = x / x.norm(dim=1, keepdim=True)
+    return E
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs[2..4]
+# --------------------------------------------------------------------------------------------------
+def bench_cfg3_varlen(vfp, model, world, rank, dev, peaks, n_videos: int, reps: int):
+    """10 000 clips, lengths randint(16, 301) seed 7, plus a few decoded inputs longer than max_frames that go through the
+    scanner's subsampling rule; clips LPT-sharded over the ranks (strong scaling, no collective); uint8 frames in HBM."""
+    from video_fingerprint_b200 import sharding
+
+    rng = np.random.default_rng(7)
+    lengths = rng.integers(16, 301, size=n_videos).tolist()
+    decoded_long = [750, 1203, 2000, 5000][: max(0, min(4, n_videos // 100))]   # decoded frame counts > max_frames = 500
+    scanner = vfp.VideoFingerprintScanner(model=model, config={"model_type": "attention"})
+    kept_long = [scanner.subsample(t) for t in decoded_long]
+    for j, keep in enumerate(kept_long):            # the first few videos are the long ones
+        lengths[j] = len(keep)
+    parts = sharding.partition_clips(lengths, world)
+    mine = parts[rank]
+    my_len = [lengths[i] for i in mine]
+    total = sum(my_len)
+    g = torch.Generator(device=dev).manual_seed(7000 + rank)
+    frames = torch.empty((total, 3, 64, 64), dtype=torch.uint8, device=dev)
+    off = 0
+    for i, t in zip(mine, my_len):
+        if i < len(decoded_long):   # a long input: synthesise the decoded video, keep the frames subsample() selects
+            full = torch.randint(0, 256, (decoded_long[i], 3, 64, 64), generator=g, device=dev, dtype=torch.uint8)
+            frames[off : off + t] = full[torch.tensor(kept_long[i], device=dev)]
+        off += t
+    chunk = 1 << 15
+    first_short = sum(t for i, t in zip(mine, my_len) if i < len(decoded_long))
+    for s in range(first_short, total, chunk):
+        e = min(total, s + chunk)
+        frames[s:e] = torch.randint(0, 256, (e - s, 3, 64, 64), generator=g, device=dev, dtype=torch.uint8)
+    torch.cuda.synchronize()
+    emb = model.fingerprint_packed(frames, my_len)   # warm-up
+    ms = timed_ms(lambda: model.fingerprint_packed(frames, my_len), reps, world, dev)
+    flops = sum_over_ranks(float(sum(clip_flops(t) for t in my_len)), world, dev)
+    frames_all = sum_over_ranks(float(total), world, dev)
+    max_frames_rank = max_over_ranks(float(total), world, dev)
+    parity = None
+    if rank == 0:   # spot check against the oracle's B=1 forward on the host: shortest, longest, a subsampled one, two more
+        from oracle.forward_oracle import forward_oracle
+
+        sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        cu = np.concatenate([[0], np.cumsum(my_len)])
+        picks = sorted({int(np.argmin(my_len)), int(np.argmax(my_len)), 0, len(mine) // 2, len(mine) - 1})
+        worst = 1.0
+        for c in picks:
+            clip = frames[cu[c] : cu[c + 1]].cpu().float().div_(255.0).unsqueeze(0)
+            want = forward_oracle(sd, clip)[0].double()
+            got = emb[c].cpu().double()
+            worst = min(worst, float(torch.dot(want, got) / (want.norm() * got.norm())))
+        parity = {"clips_checked": len(picks), "lengths": [my_len[c] for c in picks], "min_cosine_vs_oracle": worst, "ok": worst >= 0.9999}
+    del frames
+    return {
+        "value": n_videos / (ms / 1000.0), "unit": "videos/s", "videos": n_videos, "frames": int(frames_all), "ms": ms, "scaling": "strong",
+        "frames_per_s": frames_all / (ms / 1000.0), "max_frames_on_a_rank": int(max_frames_rank),
+        "lengths": "randint(16, 301) seed 7; first %d videos are decoded inputs of %s frames reduced by subsample() to %s" % (len(decoded_long), decoded_long, [len(k) for k in kept_long]),
+        "roofline": {"bound": "tensor", "achieved": flops / (ms / 1000.0) / 1e12 / world, "peak": peaks["tc_sustained"], "unit": "TFLOP/s per GPU",
+                     "frac": flops / (ms / 1000.0) / 1e12 / world / peaks["tc_sustained"]},
+        "parity": parity, "input": "uint8 frames resident in HBM, LPT partition by frame count, no collective",
+    }
+
+
+def bench_cfg4_join(vfp, world, rank, dev, peaks, n_total: int, reps: int):
+    """All-pairs threshold join over n_total rows in total: rank r owns rows [r n/G, (r+1) n/G); the timed region holds the
+    all-gather (overlapped with the rank's own diagonal block) and the row-block join against all columns."""
+    from video_fingerprint_b200 import sharding
+
+    E = make_join_data(n_total, dev, seed=11)     # same matrix on every rank (same seed); a rank only USES its rows
+    lo, hi = sharding.row_block(n_total, world, rank)
+    local = E[lo:hi].contiguous()
+    res = {}
+
+    def step():
+        res["out"] = sharding.sharded_threshold_join_device(local, 0.95)
+
+    step()
+    ms = timed_ms(step, reps, world, dev)
+    i, j, s, _ = res["out"]
+    pairs = int(sum_over_ranks(float(i.numel()), world, dev))
+    parity = None
+    if rank == 0:   # rows sampled from this rank's block against ALL columns in fp32 (blocked matmul), threshold band excluded
+        gsel = torch.Generator(device=dev).manual_seed(5)
+        rows = torch.randint(lo, hi, (512,), generator=gsel, device=dev).unique()
+        S = E[rows] @ E.T
+        want = set()
+        near = set()
+        hit = (S >= 0.95 - 1e-5).nonzero()
+        for a, b in hit.tolist():
+            v = float(S[a, b])
+            key = (int(rows[a]), b)
+            (near if abs(v - 0.95) < 1e-5 else want).add(key)
+        sel = torch.isin(i, rows)
+        got = set(zip(i[sel].tolist(), j[sel].tolist()))
+        parity = {"rows_checked": int(rows.numel()), "pairs_expected": len(want), "missing": len(want - got), "unexpected": len(got - want - near),
+                  "ok": len(want - got) == 0 and len(got - want - near) == 0}
+        del S
+    gpairs = (n_total * n_total) / (ms / 1000.0) / 1e9
+    tfl = gpairs * 512 / 1000.0 / world
+    del E
+    return {
+        "value": gpairs, "unit": "Gpairs/s", "n": n_total, "rows_per_gpu": hi - lo, "threshold": 0.95, "pairs_found": pairs, "ms": ms, "scaling": "strong",
+        "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tc_burst"], "unit": "TFLOP/s per GPU", "frac": tfl / peaks["tc_burst"],
+                     "frac_of_sustained": tfl / peaks["tc_sustained"]},
+        "parity": parity,
+        "note": "one GPU joins n x n" if world == 1 else f"row-block sharded over {world} GPUs: NCCL all-gather of the fp32 shards overlapped with the own-column block, then the remaining columns; all inside the timed region",
+    }
+
+
+def bench_cfg5_topk(vfp, world, rank, dev, peaks, n_db: int, n_q: int, k: int, reps: int):
+    """Flat inner-product top-k, queries sharded over the ranks, database replicated. The database is
+    resident before the timed region (the reference's index.add, fingerprint.py:525); the search (index.search, :528) is timed."""
+    db = make_unit_rows(n_db, dev, seed=21)
+    gq = torch.Generator(device=dev).manual_seed(22)
+    Q = torch.randn((n_q, 256), generator=gq, device=dev)
+    Q = Q / Q.norm(dim=1, keepdim=True)
+    n_copy = n_q // 100                                       # 1 % of the queries are noisy copies of database rows
+    src = torch.randint(0, n_db, (n_copy,), generator=gq, device=dev)
+    v = db[src] + 0.01 * torch.randn((n_copy, 256), generator=gq, device=dev)
+    Q[:n_copy] = v / v.norm(dim=1, keepdim=True)
+    n_tie = min(1000, n_copy, n_db // 4)                             # exact duplicates inside the database => exact score ties
+    db[n_db - n_tie :] = db[src[:n_tie]]
+    per = -(-n_q // world)
+    q_local = Q[rank * per : min(n_q, (rank + 1) * per)].contiguous()
+    res = {}
+
+    def step():
+        res["out"] = vfp.topk_inner_product_device(q_local, db, k)
+
+    step()
+    ms = timed_ms(step, reps, world, dev)
+    S, I = res["out"]
+    parity = None
+    if rank == 0:
+        nchk = min(64, q_local.shape[0])
+        ref = q_local[:nchk] @ db.T
+        ts, ti = torch.topk(ref, k + 8, dim=1)
+        ts, ti = ts.cpu().numpy(), ti.cpu().numpy()
+        gotS, gotI = S[:nchk].cpu().numpy(), I[:nchk].cpu().numpy()
+        exact = flips = bad = 0
+        for r in range(nchk):
+            order = np.lexsort((ti[r], -ts[r]))[:k]
+            wi, ws = ti[r][order], ts[r][order]
+            if np.array_equal(wi, gotI[r]):
+                exact += 1
+            elif np.allclose(ws, gotS[r], atol=2e-6) and all(abs(ref[r, int(a)].item() - float(b)) <= 2e-6 for a, b in zip(gotI[r], gotS[r])):
+                flips += 1   # same scores to fp32 summation order; indices differ only among (near-)ties
+            else:
+                bad += 1
+        parity = {"queries_checked": nchk, "identical": exact, "tie_order_only": flips, "wrong": bad, "ok": bad == 0}
+        del ref
+    tfl = 2.0 * n_q * n_db * 256 / (ms / 1000.0) / 1e12 / world
+    del db, Q
+    return {
+        "value": n_q / (ms / 1000.0), "unit": "queries/s", "n_db": n_db, "n_q": n_q, "k": k, "ms": ms, "scaling": "strong", "queries_per_gpu": int(q_local.shape[0]),
+        "gpairs_per_s": n_q * n_db / (ms / 1000.0) / 1e9,
+        "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tc_burst"], "unit": "TFLOP/s per GPU", "frac": tfl / peaks["tc_burst"],
+                     "frac_of_sustained": tfl / peaks["tc_sustained"]},
+        "parity": parity, "note": "queries sharded, database replicated and resident; fp32-exact results (bf16 tensor-core screen + fp32 re-score + exactness proof)",
+    }
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
 def run_ours(args):
     import video_fingerprint_b200 as vfp
-    from video_fingerprint_b200 import _native
+    from video_fingerprint_b200 import _native, sharding
 
-    world, rank, local = dist_setup(args.gpus)
+    world, rank, local = dist_setup()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     lib = _native.load()
-    if args.stem_pass:
-        lib.vfp_set_tuning(0, args.stem_pass)
-    if args.two_kernel_stem:
-        lib.vfp_set_tuning(1, 0)
-    if args.stem_mode >= 0:
-        lib.vfp_set_tuning(1, args.stem_mode)
     for kv in args.tuning:
         k, v = kv.split("=")
-        lib.vfp_set_tuning(int(k), int(v))
-    if args.conv_pass:
-        lib.vfp_set_tuning(3, args.conv_pass)
+        if lib.vfp_set_tuning(int(k), int(v)) != 0:
+            raise SystemExit(f"bench.py: vfp_set_tuning({k}, {v}) rejected")
     peaks = load_peaks()
 
     n_clips = args.clips
     torch.manual_seed(0)
     model = vfp.create_model("attention").eval()
-    model.frames_per_pass = args.frames_per_pass
+    if args.frames_per_pass:
+        model.frames_per_pass = args.frames_per_pass
+    if args.pipelines:
+        model.pipelines = args.pipelines
+    lib.vfp_set_tuning(9, int(model.pipelines))
     lengths = [T_FRAMES] * n_clips
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     frames = torch.empty((n_clips * T_FRAMES, 3, 64, 64), dtype=torch.bfloat16, device=dev)
@@ -269,56 +481,49 @@ def run_ours(args):
     barrier(world)
     t_end = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    clocks = sampler.window(t_begin, t_end) if rank == 0 else None
     lib.vfp_profile_read(stage_ms, 32, C.byref(launches), 1)
     gpu_launches = int(launches.value)
-    # per-kernel times: one more step with the library's stage profiler on (CUDA events between the stages,
-    # on the launching stream); kept out of the timed region because draining events stalls the launch thread
-    lib.vfp_profile_enable(1)
-    emb = step()
-    torch.cuda.synchronize()
-    lib.vfp_profile_read(stage_ms, 32, C.byref(launches), 1)
-    lib.vfp_profile_enable(0)
     ms = max_over_ranks(ms, world, dev)
     value = world * n_clips * args.steps / (ms / 1000.0)
+
+    # ---- per-kernel times INSIDE a hot loop: the library's stage profiler (CUDA events between the stages on the launching
+    # stream) stays on for `prof_steps` back-to-back steps that directly follow the timed region, so the clocks are the
+    # power-capped ones of a long run. Profiling forces ONE pipeline (stages of two passes in flight would overlap and the
+    # event pairs would measure queueing), hence the loop is timed on its own and sum(stages) is compared with ITS step time.
+    prof_steps = max(2, min(args.steps, 5))
+    lib.vfp_profile_enable(1)
+    step()   # first profiled step re-sizes nothing but settles the single-pipeline schedule
+    torch.cuda.synchronize()
+    lib.vfp_profile_read(stage_ms, 32, C.byref(launches), 1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tp_begin = time.perf_counter()
+    p0.record()
+    for _ in range(prof_steps):
+        step()
+    p1.record()
+    torch.cuda.synchronize()
+    tp_end = time.perf_counter()
+    prof_ms_per_step = p0.elapsed_time(p1) / prof_steps
+    lib.vfp_profile_read(stage_ms, 32, C.byref(launches), 1)
+    lib.vfp_profile_enable(0)
+    prof_clocks = sampler.window(tp_begin, tp_end) if rank == 0 else None
     n_stage = lib.vfp_profile_num_stages()
-    stages = {lib.vfp_profile_stage_name(i).decode(): stage_ms[i] for i in range(n_stage)}
+    stages = {lib.vfp_profile_stage_name(i).decode(): stage_ms[i] / prof_steps for i in range(n_stage)}
 
     # ---- end-to-end through the public API with host uint8 frames (pinned), copies inside the timed region ----
     e2e = None
     if not args.no_e2e:
-        pool_clips = min(n_clips, 1000)
-        host = torch.empty((pool_clips * T_FRAMES, 3, 64, 64), dtype=torch.uint8).pin_memory()
-        host.random_(0, 256)
-        sub = min(pool_clips, 500)  # clips per H2D chunk (two device buffers, copy of chunk i+1 overlaps compute of i)
-        dbuf = [torch.empty((sub * T_FRAMES, 3, 64, 64), dtype=torch.uint8, device=dev) for _ in range(2)]
-        out_host = torch.empty((n_clips, 256), dtype=torch.float32).pin_memory()
-        copy_stream = torch.cuda.Stream(dev)
-        main = torch.cuda.current_stream(dev)
+        host = torch.empty((n_clips * T_FRAMES, 3, 64, 64), dtype=torch.uint8, pin_memory=True)
+        blk = min(host.shape[0], 64 * T_FRAMES * 16)
+        host[:blk].random_(0, 256)
+        for s in range(blk, host.shape[0], blk):   # replicate the random block (filling 7.9 GB with the CPU generator takes too long)
+            e = min(host.shape[0], s + blk)
+            host[s:e] = host[: e - s]
+        out_host = torch.empty((n_clips, 256), dtype=torch.float32, pin_memory=True)
 
         def e2e_step():
-            done, i = 0, 0
-            ready = [torch.cuda.Event(), torch.cuda.Event()]
-            free = [torch.cuda.Event(), torch.cuda.Event()]
-            for ev in free:
-                ev.record(main)
-            while done < n_clips:
-                n = min(sub, n_clips - done)
-                off = (done % pool_clips)
-                if off + n > pool_clips:
-                    off = 0
-                b = i & 1
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(free[b])
-                    dbuf[b][: n * T_FRAMES].copy_(host[off * T_FRAMES : (off + n) * T_FRAMES], non_blocking=True)
-                    ready[b].record(copy_stream)
-                main.wait_event(ready[b])
-                e = model.fingerprint_packed(dbuf[b][: n * T_FRAMES], [T_FRAMES] * n)
-                out_host[done : done + n].copy_(e, non_blocking=True)
-                free[b].record(main)
-                done += n
-                i += 1
-            main.synchronize()
+            model.fingerprint_host(host, lengths, chunk_frames=500 * T_FRAMES, out=out_host)   # returns after the D2H copy
 
         e2e_step()
         barrier(world)
@@ -331,128 +536,88 @@ def run_ours(args):
         e2e = {
             "value": world * n_clips * e2e_steps / dt, "unit": "videos/s",
             "h2d_bytes_per_step": n_clips * T_FRAMES * 12288, "d2h_bytes_per_step": n_clips * 256 * 4,
-            "input": "uint8 frames in pinned host memory, 500-clip chunks double-buffered on a copy stream", "steps": e2e_steps,
+            "input": "uint8 frames in pinned host memory through model.fingerprint_host (500-clip chunks, double-buffered on a copy stream)", "steps": e2e_steps,
+            "pcie_gbs": n_clips * T_FRAMES * 12288 * e2e_steps / dt / 1e9,
         }
-        del dbuf, host
+        del host
+    del frames
+    torch.cuda.empty_cache()
 
-    # ---- similarity join (second half of the BASELINE metric) ----
-    # N = 1: one GPU joins n x n. N > 1 (BASELINE configs[3] layout): every rank owns a row block of `join_n` rows of
-    # the (N * join_n)-row matrix; the timed region holds the NCCL all-gather of the shards AND the row-block join
-    # against all columns (global pair indices through q_row0), max over ranks.
+    # ---- similarity join, weak scaling (second half of the BASELINE metric): join_n rows per GPU ----
     join = None
     if not args.no_join:
         n_local = args.join_n
-        n_total = n_local * world
         E_local = make_join_data(n_local, dev, seed=11 + rank)
-        if world > 1:
-            import torch.distributed as dist
+        res = {}
 
-            E_full = torch.empty((n_total, 256), dtype=torch.float32, device=dev)
+        def join_step():
+            res["out"] = sharding.sharded_threshold_join_device(E_local, 0.95)
 
-            def join_step(capacity=None):
-                dist.all_gather_into_tensor(E_full, E_local)
-                return vfp.threshold_join_device(E_full, 0.95, q=E_local, q_row0=rank * n_local, capacity=capacity)
-        else:
-            def join_step(capacity=None):
-                return vfp.threshold_join_device(E_local, 0.95, capacity=capacity)
-
-        ii, jj, ss = join_step()  # warm-up + sizes
-        cap = int(ii.numel()) + 4096
-        torch.cuda.synchronize()
-        barrier(world)
-        j0, j1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        j0.record()
-        reps = 3
-        for _ in range(reps):
-            ii, jj, ss = join_step(cap)
-        j1.record()
-        torch.cuda.synchronize()
-        jms = max_over_ranks(j0.elapsed_time(j1) / reps, world, dev)
-        pairs_found = int(max_over_ranks(float(ii.numel()), world, dev)) if world == 1 else None
-        if world > 1:
-            t = torch.tensor([float(ii.numel())], dtype=torch.float64, device=dev)
-            dist.all_reduce(t)
-            pairs_found = int(t.item())
+        join_step()
+        jms = timed_ms(join_step, 3, world, dev)
+        n_total = res["out"][3]
+        pairs_found = int(sum_over_ranks(float(res["out"][0].numel()), world, dev))
         gpairs = (n_total * n_total) / (jms / 1000.0) / 1e9
         tfl = gpairs * 512 / 1000.0 / world
         join = {
-            "value": gpairs, "unit": "Gpairs/s", "n": n_total, "rows_per_gpu": n_local, "threshold": 0.95, "pairs_found": pairs_found, "ms": jms,
-            "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tc_burst"], "unit": "TFLOP/s per GPU", "frac": tfl / peaks["tc_burst"], "traffic": None},
+            "value": gpairs, "unit": "Gpairs/s", "n": n_total, "rows_per_gpu": n_local, "threshold": 0.95, "pairs_found": pairs_found, "ms": jms, "scaling": "weak",
+            "roofline": {"bound": "tensor", "achieved": tfl, "peak": peaks["tc_burst"], "unit": "TFLOP/s per GPU", "frac": tfl / peaks["tc_burst"],
+                         "frac_of_sustained": tfl / peaks["tc_sustained"], "traffic": None},
             "note": ("one GPU joins n x n" if world == 1 else
-                     f"row-block sharded: NCCL all-gather of {world} x ({n_local}, 256) fp32 shards + each rank joins its {n_local} rows against all {n_total} columns, both inside the timed region"),
+                     f"row-block sharded: NCCL all-gather of {world} x ({n_local}, 256) fp32 shards overlapped with the own-column block + the remaining columns, all inside the timed region"),
         }
-        del E_local
+        del E_local, res
+        torch.cuda.empty_cache()
 
-    # ---- the neighbouring steps of SURVEY.md section 8(f), timed briefly (rank 0, device-resident inputs, CUDA events) ----
-    extras = None
-    if not args.no_extras and rank == 0:
-        extras = {}
-
-        def timed(fn, reps=3):
-            fn()
-            torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            for _ in range(reps):
-                fn()
-            b.record()
-            torch.cuda.synchronize()
-            return a.elapsed_time(b) / reps
-
+    def guarded(fn, *a):
         try:
-            dec = torch.randint(0, 256, (64, 1080, 1920, 3), dtype=torch.uint8, device=dev)   # one video's decoded 1080p frames
-            ms_pre = timed(lambda: vfp.preprocess_frames_device(dec))
-            extras["preprocess_1080p"] = {"frames_per_s": 64 / ms_pre * 1e3, "ms_per_64_frames": ms_pre, "hbm_gbs": 64 * 1088 * 1080 * 3 / ms_pre / 1e6,
-                                          "what": "INTER_AREA resize to a short side of 64 + centre crop (fingerprint.py:186-214), bit-exact with cv2"}
-            del dec
-            g3 = torch.Generator(device=dev).manual_seed(5)
-            nm = 8192
-            Em = torch.randn((nm, 256), generator=g3, device=dev)
-            Em = Em / Em.norm(dim=1, keepdim=True)
-            ids = np.repeat(np.arange(nm // 2), 2)
-            ms_met = timed(lambda: (vfp.compute_retrieval_metrics(Em, ids), vfp.compute_discrimination_metrics(Em, ids)), reps=2)
-            extras["trainer_metrics"] = {"embeddings": nm, "ms_both_functions": ms_met, "what": "R@k, mAP, P/R/F1/FPR, AUC-ROC (train.py:285-358, 439-481), host bookkeeping included"}
-            m3 = vfp.create_model("3d").eval()
-            n3 = min(2048, n_clips)
-            x3 = frames[: n3 * T_FRAMES].view(n3, T_FRAMES, 3, 64, 64)
-            ms_3d = timed(lambda: m3(x3))
-            extras["model_3d"] = {"videos_per_s": n3 / ms_3d * 1e3, "clips": n3, "frames": T_FRAMES, "frame_stride": 16, "what": "VideoFingerprint3D forward (model.py:406-512), bf16 frames in HBM"}
-            del m3
-        except Exception as exc:  # these are side measurements: never fail the headline line
-            extras["error"] = repr(exc)
+            out = fn(*a)
+        except Exception as exc:  # the side configurations never take the headline line down
+            out = {"error": repr(exc)}
+        torch.cuda.empty_cache()
+        return out
 
+    cfg3 = guarded(bench_cfg3_varlen, vfp, model, world, rank, dev, peaks, args.cfg3_videos, 3) if not args.no_cfg3 else None
+    cfg4 = guarded(bench_cfg4_join, vfp, world, rank, dev, peaks, args.cfg4_rows, 2) if not args.no_cfg4 else None
+    cfg5 = guarded(bench_cfg5_topk, vfp, world, rank, dev, peaks, args.cfg5_db, args.cfg5_q, 10, 2) if not args.no_cfg5 else None
+
+    if rank == 0:
+        sampler.stop()
     if rank != 0:
         return
     # ---- roofline of the dominant kernel ----
-    dom = max((k for k in stages if k in STAGE_FLOPS or k in STAGE_BYTES), key=lambda k: stages[k])
-    token_passes = -(-n_clips * T_FRAMES // args.frames_per_pass)
-    conv_passes = -(-min(n_clips * T_FRAMES, args.frames_per_pass) // 16384) * token_passes
-    launches_per_step = conv_passes if dom.startswith("conv") or dom == "stem_fused" else token_passes * (4 if dom.endswith("gemm") or dom in ("attention", "mlp1_gemm_gelu") else 1)
+    known = [k for k in stages if (k in STAGE_FLOPS or k in STAGE_BYTES) and stages[k] > 0]
+    dom = max(known, key=lambda k: stages[k])
+    sum_stages = sum(stages.values())
+    conv_launches = -(-n_clips * T_FRAMES // 16384)
     dom_ms = stages[dom]
     tflops = STAGE_FLOPS.get(dom, 0) * n_clips / (dom_ms / 1000.0) / 1e12
     gbs = STAGE_BYTES.get(dom, 0) * n_clips / (dom_ms / 1000.0) / 1e9
     frac_t, frac_h = tflops / peaks["tc_sustained"], gbs / peaks["hbm"]
     hbm_bound = frac_h > frac_t  # the binding roofline is the one the kernel sits closer to
-    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/r01_v6_stem_ts_full.txt:
-    # dram__bytes_read.sum + dram__bytes_write.sum of one stem launch over a 16 384-frame conv pass); below the algorithmic
-    # 939.5 MB because the tail of the output is still in L2 when the kernel ends
+    # DRAM bytes per launch of the stem from the committed `ncu --set full` capture (profiles/r01_v6_stem_ts_full.txt:
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch over a 16 384-frame conv pass)
     ncu_traffic = {"stem_fused": 402.787584e6 + 488.215040e6}
+    whole_tfl = value / world * FLOPS_PER_CLIP / 1e12
     roofline = {
         "bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
         "achieved": gbs if hbm_bound else tflops, "peak": peaks["hbm"] if hbm_bound else peaks["tc_sustained"],
         "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": frac_h if hbm_bound else frac_t,
+        "frac_of_burst": None if hbm_bound else tflops / peaks["tc_burst"],
         "traffic": ncu_traffic.get(dom) if (n_clips * T_FRAMES) >= 16384 else None,
         "traffic_note": "bytes per launch (one 16 384-frame conv pass) from the committed ncu capture of this kernel; algorithmic bytes per launch = %.1f MB" % (STAGE_BYTES.get(dom, 0) / T_FRAMES * 16384 / 1e6),
-        "peak_source": f"{peaks['source']} ({'HBM copy bandwidth' if hbm_bound else 'sustained bf16, kernel timed inside a long step'})",
+        "peak_source": f"{peaks['source']} ({'HBM copy bandwidth' if hbm_bound else 'sustained bf16: the kernel is timed inside a long hot loop'})",
+        "timing": f"stage events inside a {prof_steps}-step hot loop that follows the timed region (single pipeline): {prof_ms_per_step:.2f} ms/step, sum of stages {sum_stages:.2f} ms",
+        "profiled_ms_per_step": prof_ms_per_step, "sum_of_stages_ms": sum_stages, "profile_clocks": prof_clocks,
         "other_roofline": {"tensor_tflops": tflops, "tensor_frac": frac_t, "hbm_gbs": gbs, "hbm_frac": frac_h},
-        "launches_per_step": launches_per_step, "ms_per_step_in_kernel": dom_ms,
+        "launches_per_step": conv_launches, "ms_per_step_in_kernel": dom_ms,
         "algorithmic_per_clip": {"flops": STAGE_FLOPS.get(dom), "bytes": STAGE_BYTES.get(dom)},
-        "whole_step": {"achieved": value / world * FLOPS_PER_CLIP / 1e12, "frac": value / world * FLOPS_PER_CLIP / 1e12 / peaks["tc_sustained"], "unit": "TFLOP/s"},
+        "whole_step": {"achieved": whole_tfl, "unit": "TFLOP/s", "frac": whole_tfl / peaks["tc_sustained"], "frac_of_burst": whole_tfl / peaks["tc_burst"]},
         "per_stage": {
             k: {"ms": round(stages[k], 3),
                 "tflops": round(STAGE_FLOPS[k] * n_clips / (stages[k] / 1000.0) / 1e12, 1) if k in STAGE_FLOPS and stages[k] > 0 else None,
                 "gbs": round(STAGE_BYTES[k] * n_clips / (stages[k] / 1000.0) / 1e9, 1) if k in STAGE_BYTES and stages[k] > 0 else None}
-            for k in stages
+            for k in stages if stages[k] > 0
         },
     }
     line = {
@@ -460,10 +625,12 @@ def run_ours(args):
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {
             "workload": f"batched fingerprint forward: {n_clips} synthetic clips x {T_FRAMES} frames @ 64x64 per GPU, bf16 frames resident in HBM, random-init weights (BASELINE configs[1])",
-            "frames_per_pass": args.frames_per_pass, "l2": f"inputs ({n_clips * T_FRAMES * 24576 / 1e9:.1f} GB) and per-pass activations exceed the 126 MB L2; no flush needed",
+            "frames_per_pass": model.frames_per_pass, "pipelines": model.pipelines,
+            "l2": f"inputs ({n_clips * T_FRAMES * 24576 / 1e9:.1f} GB) and per-pass activations exceed the 126 MB L2; no flush needed",
             "parallelism": f"clips sharded over {world} GPU(s), no data-path collective",
         },
-        "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "stage_ms_per_step": stages, "join": join, "extras": extras, "clocks": clocks,
+        "e2e": e2e, "gpu_launches": gpu_launches, "roofline": roofline, "stage_ms_per_step": {k: v for k, v in stages.items() if v > 0},
+        "join": join, "cfg3_varlen": cfg3, "cfg4_join": cfg4, "cfg5_topk": cfg5, "clocks": clocks,
     }
     if not args.no_cpu and world == 1:
         r, n, dt = cpu_reference_rate(args.cpu_seconds, 2048)
@@ -481,19 +648,25 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=N_CLIPS)
-    ap.add_argument("--frames-per-pass", type=int, default=1 << 20)
+    ap.add_argument("--frames-per-pass", type=int, default=0, help="frames per token pass (default: the model's)")
+    ap.add_argument("--pipelines", type=int, default=0, help="token passes in flight (default: the model's)")
     ap.add_argument("--join-n", type=int, default=262_144)
+    ap.add_argument("--cfg3-videos", type=int, default=10_000)
+    ap.add_argument("--cfg4-rows", type=int, default=1_048_576)
+    ap.add_argument("--cfg5-db", type=int, default=10_000_000)
+    ap.add_argument("--cfg5-q", type=int, default=100_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
-    ap.add_argument("--stem-pass", type=int, default=0, help="experiment: frames per conv1+conv2 stem pass")
-    ap.add_argument("--two-kernel-stem", action="store_true", help="experiment: stand-alone conv1 + conv2 kernels instead of the fused stem")
-    ap.add_argument("--stem-mode", type=int, default=-1, help="experiment: 0 two kernels, 1 fused stem with mma.sync conv1, 2 fused stem with TS-mode tcgen05 conv1")
     ap.add_argument("--tuning", action="append", default=[], help="experiment: key=value passed to vfp_set_tuning")
-    ap.add_argument("--conv-pass", type=int, default=0, help="experiment: frames per conv pass (<= 16384)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-join", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the brief preprocess / trainer-metrics / 3-D model timings")
+    ap.add_argument("--no-cfg3", action="store_true")
+    ap.add_argument("--no-cfg4", action="store_true")
+    ap.add_argument("--no-cfg5", action="store_true")
+    ap.add_argument("--forward-only", action="store_true", help="skip e2e, joins, cfg 3-5 and the CPU baseline (kernel experiments)")
     args = ap.parse_args()
+    if args.forward_only:
+        args.no_e2e = args.no_join = args.no_cpu = args.no_cfg3 = args.no_cfg4 = args.no_cfg5 = True
     if args.impl == "reference":
         run_reference(args)
         return

@@ -100,9 +100,51 @@ def test_pass_splitting_is_invisible():
     clips = make_clips(32, [40, 12, 64, 19, 50, 25, 31], "colour")
     whole = m.fingerprint_clips(clips).cpu()
     m.frames_per_pass = 70          # forces several internal passes
-    m._workspace = None
+    m._workspaces.clear()
     split = m.fingerprint_clips(clips).cpu()
     assert torch.allclose(whole, split, atol=1e-6)
+
+
+def test_pipelined_passes_and_host_upload_are_invisible():
+    """Token passes dealt onto two internal streams (model.pipelines = 2, the default) and the chunked double-buffered host
+    upload (fingerprint_host) must give what ONE pass on the caller's stream gives. 40 000 frames so that the library really
+    runs two pipelines (it needs at least two conv passes of 16 384 frames)."""
+    m = model_for(2, "stress")
+    g = torch.Generator().manual_seed(77)
+    lengths = [int(t) for t in torch.randint(10, 120, (620,), generator=g)]
+    total = sum(lengths)
+    assert total >= 2 * 16384
+    frames = torch.randint(0, 256, (total, 3, 64, 64), dtype=torch.uint8, generator=g)
+    dev = frames.cuda()
+    m.pipelines, m.frames_per_pass = 1, 1 << 20
+    one = m.fingerprint_packed(dev, lengths).cpu()
+    m.pipelines, m.frames_per_pass = 2, 9000
+    m._workspaces.clear()
+    two = m.fingerprint_packed(dev, lengths).cpu()
+    assert _native.load().vfp_device_error_word() == 0
+    assert torch.allclose(one, two, atol=1e-6)
+    host = m.fingerprint_host(frames.pin_memory(), lengths, chunk_frames=7000).cpu()
+    assert torch.allclose(one, host, atol=1e-6)
+    out = torch.empty((len(lengths), 256), dtype=torch.float32).pin_memory()
+    assert m.fingerprint_host(frames, lengths, chunk_frames=50_000, out=out) is out      # pageable source works too
+    assert torch.allclose(one, out, atol=1e-6)
+    assert torch.allclose(m.fingerprint_packed(frames, lengths).cpu(), one, atol=1e-6)  # host tensor through the generic entry
+    # spot check against the oracle (the bar of every other test here)
+    sd = make_state_dict(2, "stress")
+    cu = np.concatenate([[0], np.cumsum(lengths)])
+    for c in (0, 311, 619):
+        want = forward_oracle(sd, frames[cu[c] : cu[c + 1]].float().div(255).unsqueeze(0))
+        assert cosine(two[c], want[0]) >= COS_BAR
+
+
+def test_clip_longer_than_1024_frames():
+    """The positional table of the checkpoint (10 000 rows, model.py:77) is the only length limit."""
+    sd = make_state_dict(2, "stress")
+    m = model_for(2, "stress")
+    clips = make_clips(61, [1500, 23], "colour")
+    want = torch.stack(fingerprint_clips(sd, clips))
+    got = m.fingerprint_clips(clips).cpu()
+    assert cosine(got, want).min() >= COS_BAR
 
 
 def test_return_features_and_layout_quirk():
@@ -183,8 +225,10 @@ def test_error_behaviour():
         m.fingerprint_packed(torch.zeros(10, 3, 64, 64).cuda(), [4, 5])
     with pytest.raises(_native.NativeError, match="no frames"):
         m.fingerprint_packed(torch.zeros(10, 3, 64, 64).cuda(), [10, 0])
-    with pytest.raises(_native.NativeError, match="limit"):
-        m.fingerprint_packed(torch.zeros(1025, 3, 64, 64, dtype=torch.uint8).cuda(), [1025])
+    with pytest.raises(_native.NativeError, match="positional table"):
+        m.fingerprint_packed(torch.zeros(10001, 3, 64, 64, dtype=torch.uint8).cuda(), [10001])
+    with pytest.raises(_native.NativeError, match="CUDA devices only"):
+        vfp.VideoFingerprintScanner(model=m, device="cpu")
     m.train()
     with pytest.raises(RuntimeError, match="inference only"):
         m(torch.zeros(1, 10, 3, 64, 64).cuda())

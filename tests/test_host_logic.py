@@ -12,7 +12,7 @@ import torch
 import video_fingerprint_b200 as vfp
 from oracle import join_oracle
 from oracle.weights import make_state_dict, state_dict_digest, state_spec
-from video_fingerprint_b200 import _native
+from video_fingerprint_b200 import _native, fingerprint
 from video_fingerprint_b200.sharding import partition_clips, row_block
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -121,3 +121,21 @@ def test_save_results_schema(tmp_path):
     assert set(data["metadata"]) == {"scan_date", "total_videos", "duplicate_groups", "model_config", "model_type"}
     assert isinstance(data["fingerprints"]["a.mp4"]["embedding"], list) and len(data["fingerprints"]["a.mp4"]["embedding"]) == 256
     assert data["duplicate_groups"][0][0]["similarity"] == 1.0
+
+
+def test_topk_grouping_compares_in_float32_like_the_reference():
+    """fingerprint.py:540 compares an np.float32 score with the Python-float threshold; NumPy 2 evaluates that in float32, so
+    a score equal to np.float32(0.95) (which is < 0.95 as a double) IS a hit. Both the restatement and the product keep it."""
+    thr = 0.95
+    edge = np.float32(thr)
+    assert float(edge) < thr and bool(edge >= thr)          # the situation the rule is about
+    below = np.nextafter(edge, np.float32(0))
+    S = np.array([[1.0, edge, below], [1.0, edge, 0.1], [1.0, below, 0.2]], dtype=np.float32)
+    I = np.array([[0, 1, 2], [1, 0, 2], [2, 0, 1]], dtype=np.int64)
+    want = join_oracle.group_topk(S, I, thr)
+    got = fingerprint.group_pairs_topk(S, I, thr)
+    assert [[i for i, _ in g] for g in got] == [[i for i, _ in g] for g in want] == [[0, 1]]
+    # and the direct path's rule (np.where(row >= thr) on a float32 matrix, fingerprint.py:499) on the same score
+    pi, pj = np.array([0, 0, 1, 1]), np.array([0, 1, 0, 1])
+    ps = np.array([1.0, edge, edge, 1.0], dtype=np.float32)
+    assert [[i for i, _ in g] for g in fingerprint.group_pairs_direct(2, pi, pj, ps)] == [[0, 1]]

@@ -147,3 +147,20 @@ def test_non_unit_norm_embeddings():
     """Segment-averaged fingerprints are not unit norm (fingerprint.py:268); the screen margin scales with the norms."""
     E = planted(2000, 150, seed=5) * np.random.default_rng(6).uniform(0.5, 1.5, size=(2000, 1)).astype(np.float32)
     assert_pairs_match(vfp.threshold_join(E, 0.8), join_oracle.threshold_pairs(E, 0.8), 0.8)
+
+
+def test_join_splits_query_rows_when_candidates_exceed_the_buffer(monkeypatch):
+    """A low threshold on a duplicated corpus yields ~N^2 candidates; the host bounds the candidate buffer and splits the
+    query rows instead of allocating it (round 1 tried to allocate 12 bytes x N^2)."""
+    from video_fingerprint_b200 import fingerprint as fp
+
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((6, 256)).astype(np.float32)
+    E = base[rng.integers(0, 6, 900)] + 0.02 * rng.standard_normal((900, 256)).astype(np.float32)
+    E /= np.linalg.norm(E, axis=1, keepdims=True)
+    want = join_oracle.threshold_pairs(E, 0.9)
+    assert len(want[0]) > 100_000
+    monkeypatch.setattr(fp, "_MAX_CANDIDATES", 30_000)
+    got = fp.threshold_join(E, 0.9)
+    assert_pairs_match(got, want, 0.9, band=1e-5)
+    assert np.all(np.diff(got[0]) >= 0)

@@ -26,8 +26,6 @@ static int g_topk_prefetch = 0;
 constexpr int kTopKCand = 64;        // approximate candidates kept per query row
 constexpr int kTopKMaxK = 32;
 constexpr int kTopKMaxSegments = 32;
-constexpr int kTopKBucket = 512;     // exact-fallback candidates per flagged row
-constexpr int kTopKMaxFlagged = 8192;
 
 // Candidate list of one query row = a 64-entry binary heap in shared memory with the WORST kept candidate at the root
 // ((score asc, index desc) order, so the root is what a better newcomer must evict and its score is the admission
@@ -135,7 +133,7 @@ __global__ void __launch_bounds__(256)
 topk_merge_rescore_kernel(const float* __restrict__ q, const float* __restrict__ db, long long n_q, long long n_db, int k,
                           int n_segments, const float* __restrict__ part_s, const int* __restrict__ part_i, float margin,
                           float* __restrict__ out_s, long long* __restrict__ out_idx, int* __restrict__ flagged_rows,
-                          float* __restrict__ flagged_tau, unsigned long long* __restrict__ flags /*[0]=flagged,[1]=overflow*/) {
+                          float* __restrict__ flagged_tau, unsigned long long* __restrict__ flags /*[0] = flagged rows*/) {
   const int lane = threadIdx.x & 31;
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= n_q) return;
@@ -209,78 +207,111 @@ topk_merge_rescore_kernel(const float* __restrict__ q, const float* __restrict__
   // ---- proof of exactness ----
   const bool list_is_everything = i_last < 0;  // fewer than 64 database rows exist in total
   const bool proven = list_is_everything || (kth_exact > a_last + margin);
-  if (!proven && lane == 0) {
+  if (!proven && lane == 0) {   // the flag lists hold one slot per query row: they cannot overflow
     const unsigned long long slot = atomicAdd(&flags[0], 1ull);
-    if (slot < (unsigned long long)kTopKMaxFlagged) {
-      flagged_rows[slot] = (int)row;
-      flagged_tau[slot] = kth_exact;
-    } else {
-      atomicAdd(&flags[1], 1ull);
-    }
+    flagged_rows[slot] = (int)row;
+    flagged_tau[slot] = kth_exact;
   }
 }
 
-// Exact fallback, pass 1: for every flagged query, scan ALL database rows in fp32 and bucket those with
-// score >= tau (the exact k-th score among the screened candidates - a lower bound of the true k-th score).
+// Exact fallback, pass 1. A flagged query row is one whose 64 screened candidates could not be PROVEN to contain the exact
+// top k (dense neighbourhoods, large groups of identical embeddings - both normal in a duplicate detector). Such a row is
+// re-searched with a plain fp32 scan of the whole database; nothing here has a capacity a data set can overflow:
+// block (slice s, flagged row f) scans database rows s*8 + warp, + 128, ... and every warp keeps its own exact best-32 list
+// ((score desc, index asc), one entry per lane, sorted insertion with one ballot + one shuffle), the block merges its eight
+// lists and writes its k best to part[f][s][0..k). tau (the exact k-th score among the screened candidates, a lower bound
+// of the true k-th score) only prunes. Flagged rows are processed in batches of kTopKBatch so the part buffer stays small.
+constexpr int kTopKSlices = 16;
+constexpr int kTopKBatch = 8192;
+
 __global__ void __launch_bounds__(256)
-topk_fallback_scan_kernel(const float* __restrict__ q, const float* __restrict__ db, long long n_db,
+topk_fallback_scan_kernel(const float* __restrict__ q, const float* __restrict__ db, long long n_db, int k, long long batch0,
                           const int* __restrict__ flagged_rows, const float* __restrict__ flagged_tau,
-                          const unsigned long long* __restrict__ flags, int* __restrict__ bucket_cnt,
-                          float* __restrict__ bucket_s, int* __restrict__ bucket_i, unsigned long long* __restrict__ flags_rw) {
-  const int lane = threadIdx.x & 31;
-  const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  unsigned long long nf = flags[0];
-  if (nf > (unsigned long long)kTopKMaxFlagged) nf = kTopKMaxFlagged;
-  for (unsigned long long f = 0; f < nf; ++f) {
+                          const unsigned long long* __restrict__ flags, float* __restrict__ part_s, int* __restrict__ part_i) {
+  __shared__ float ms[8 * 32];
+  __shared__ int mi[8 * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nf = (long long)flags[0];
+  const int slice = blockIdx.x;
+  for (long long f = batch0 + blockIdx.y; f < nf && f < batch0 + kTopKBatch; f += gridDim.y) {
     const int row = flagged_rows[f];
     const float tau = flagged_tau[f];
     float qv[8];
     const float4* r = reinterpret_cast<const float4*>(q + (size_t)row * 256) + lane * 2;
     const float4 a = r[0], b = r[1];
     qv[0] = a.x; qv[1] = a.y; qv[2] = a.z; qv[3] = a.w; qv[4] = b.x; qv[5] = b.y; qv[6] = b.z; qv[7] = b.w;
-    for (long long j = warp0; j < n_db; j += warps) {
-      const float s = warp_dot256(qv, db, j, lane);
-      if (lane == 0 && s >= tau) {
-        const int slot = atomicAdd(&bucket_cnt[f], 1);
-        if (slot < kTopKBucket) {
-          bucket_s[f * kTopKBucket + slot] = s;
-          bucket_i[f * kTopKBucket + slot] = (int)j;
-        } else if (slot == kTopKBucket) {
-          atomicAdd(&flags_rw[1], 1ull);
+    float ls = -INFINITY;       // this lane's entry of the warp's sorted list (lane 0 = best)
+    int li = 0x7fffffff;
+    float ws = -INFINITY;       // entry k-1 (the admission threshold), known to every lane
+    int wi = 0x7fffffff;
+    for (long long j = (long long)slice * 8 + warp; j < n_db; j += kTopKSlices * 8) {
+      const float sc = warp_dot256(qv, db, j, lane);
+      if (sc >= tau && topk_better(sc, (int)j, ws, wi)) {   // warp-uniform
+        const int pos = __popc(__ballot_sync(0xffffffffu, topk_better(ls, li, sc, (int)j)));
+        const float us = __shfl_up_sync(0xffffffffu, ls, 1);
+        const int ui = __shfl_up_sync(0xffffffffu, li, 1);
+        if (lane == pos) { ls = sc; li = (int)j; }
+        else if (lane > pos) { ls = us; li = ui; }
+        ws = __shfl_sync(0xffffffffu, ls, k - 1);
+        wi = __shfl_sync(0xffffffffu, li, k - 1);
+      }
+    }
+    __syncthreads();   // the previous row's merge has been read
+    ms[warp * 32 + lane] = ls;
+    mi[warp * 32 + lane] = li;
+    __syncthreads();
+    {
+      const float es = ms[threadIdx.x];
+      const int ei = mi[threadIdx.x];
+      if (ei != 0x7fffffff) {
+        int rank = 0;
+        for (int o = 0; o < 256; ++o) rank += topk_better(ms[o], mi[o], es, ei) ? 1 : 0;
+        if (rank < k) {
+          const size_t base = ((size_t)(f - batch0) * kTopKSlices + slice) * kTopKMaxK;
+          part_s[base + rank] = es;
+          part_i[base + rank] = ei;
         }
       }
     }
   }
 }
 
-// Exact fallback, pass 2: rank each flagged row's bucket and overwrite its output row.
+// Exact fallback, pass 2: merge the slices' lists of each flagged row and overwrite its output row.
 __global__ void __launch_bounds__(128)
-topk_fallback_rank_kernel(int k, const int* __restrict__ flagged_rows, const unsigned long long* __restrict__ flags,
-                          const int* __restrict__ bucket_cnt, const float* __restrict__ bucket_s, const int* __restrict__ bucket_i,
-                          float* __restrict__ out_s, long long* __restrict__ out_idx) {
-  unsigned long long nf = flags[0];
-  if (nf > (unsigned long long)kTopKMaxFlagged) nf = kTopKMaxFlagged;
-  for (unsigned long long f = blockIdx.x; f < nf; f += gridDim.x) {
+topk_fallback_rank_kernel(int k, long long batch0, const int* __restrict__ flagged_rows, const unsigned long long* __restrict__ flags,
+                          const float* __restrict__ part_s, const int* __restrict__ part_i, float* __restrict__ out_s,
+                          long long* __restrict__ out_idx) {
+  const long long nf = (long long)flags[0];
+  constexpr int n = kTopKSlices * kTopKMaxK;
+  for (long long f = batch0 + blockIdx.x; f < nf && f < batch0 + kTopKBatch; f += gridDim.x) {
     const int row = flagged_rows[f];
-    const int n = min(bucket_cnt[f], kTopKBucket);
-    const float* bs = bucket_s + f * kTopKBucket;
-    const int* bi = bucket_i + f * kTopKBucket;
+    const float* bs = part_s + (size_t)(f - batch0) * n;
+    const int* bi = part_i + (size_t)(f - batch0) * n;
     for (int c = threadIdx.x; c < n; c += blockDim.x) {
-      const float s = bs[c];
       const int idx = bi[c];
+      if (idx < 0 || (c & (kTopKMaxK - 1)) >= k) continue;   // empty slot / beyond the slice's k best
+      const float sc = bs[c];
       int rank = 0;
-      for (int o = 0; o < n; ++o) rank += topk_better(bs[o], bi[o], s, idx) ? 1 : 0;
+      for (int o = 0; o < n; ++o) {
+        const int oi = bi[o];
+        if (oi >= 0 && (o & (kTopKMaxK - 1)) < k) rank += topk_better(bs[o], oi, sc, idx) ? 1 : 0;
+      }
       if (rank < k) {
-        out_s[(size_t)row * k + rank] = s;
+        out_s[(size_t)row * k + rank] = sc;
         out_idx[(size_t)row * k + rank] = idx;
       }
     }
   }
 }
 
+// part_i = -1 everywhere (a slice with fewer than k rows >= tau leaves empty slots)
+__global__ void topk_fill_kernel(int* __restrict__ p, long long n, int v, const unsigned long long* __restrict__ flags, long long batch0) {
+  if ((long long)flags[0] <= batch0) return;   // no flagged row in this batch
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
 struct TopKWs {
-  size_t qbf, dbbf, part_s, part_i, flagged_rows, flagged_tau, bucket_cnt, bucket_s, bucket_i, flags, total;
+  size_t qbf, dbbf, part_s, part_i, flagged_rows, flagged_tau, fb_s, fb_i, flags, total;
   int n_segments;
   long long rows_padded;
 };
@@ -299,15 +330,15 @@ inline TopKWs topk_ws_layout(int64_t n_q, int64_t n_db) {
   while (seg < kTopKMaxSegments && m_tiles * seg < 4 * 148 && seg * 2 <= n_tiles) seg *= 2;
   L.n_segments = seg;
   L.rows_padded = m_tiles * 128;
+  const int64_t batch = std::min<int64_t>(n_q, kTopKBatch);
   L.qbf = take((size_t)n_q * 512);
   L.dbbf = take((size_t)n_db * 512);
   L.part_s = take((size_t)L.rows_padded * seg * kTopKCand * 4);
   L.part_i = take((size_t)L.rows_padded * seg * kTopKCand * 4);
-  L.flagged_rows = take((size_t)kTopKMaxFlagged * 4);
-  L.flagged_tau = take((size_t)kTopKMaxFlagged * 4);
-  L.bucket_cnt = take((size_t)kTopKMaxFlagged * 4);
-  L.bucket_s = take((size_t)kTopKMaxFlagged * kTopKBucket * 4);
-  L.bucket_i = take((size_t)kTopKMaxFlagged * kTopKBucket * 4);
+  L.flagged_rows = take((size_t)n_q * 4);
+  L.flagged_tau = take((size_t)n_q * 4);
+  L.fb_s = take((size_t)batch * kTopKSlices * kTopKMaxK * 4);
+  L.fb_i = take((size_t)batch * kTopKSlices * kTopKMaxK * 4);
   L.flags = take(64);
   L.total = off;
   return L;
@@ -328,16 +359,14 @@ inline int topk_run(const float* q, const float* db, int64_t n_q, int64_t n_db, 
   int* part_i = reinterpret_cast<int*>(ws + L.part_i);
   int* flagged_rows = reinterpret_cast<int*>(ws + L.flagged_rows);
   float* flagged_tau = reinterpret_cast<float*>(ws + L.flagged_tau);
-  int* bucket_cnt = reinterpret_cast<int*>(ws + L.bucket_cnt);
-  float* bucket_s = reinterpret_cast<float*>(ws + L.bucket_s);
-  int* bucket_i = reinterpret_cast<int*>(ws + L.bucket_i);
+  float* fb_s = reinterpret_cast<float*>(ws + L.fb_s);
+  int* fb_i = reinterpret_cast<int*>(ws + L.fb_i);
   unsigned long long* flags = reinterpret_cast<unsigned long long*>(ws + L.flags);
   auto ck = [&](cudaError_t e, const char* what) {
     if (e != cudaSuccess) { *err = std::string(what) + ": " + cudaGetErrorString(e); return true; }
     return false;
   };
-  if (ck(cudaMemsetAsync(flags, 0, 64, st), "memset") || ck(cudaMemsetAsync(bucket_cnt, 0, (size_t)kTopKMaxFlagged * 4, st), "memset"))
-    return 1;
+  if (ck(cudaMemsetAsync(flags, 0, 64, st), "memset")) return 1;
   f32_to_bf16_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, st>>>(q, qbf, n_q * 32);
   if (!self) f32_to_bf16_kernel<<<(unsigned)((n_db * 32 + 255) / 256), 256, 0, st>>>(db, dbbf, n_db * 32);
   CUtensorMap ta, tb;
@@ -356,10 +385,17 @@ inline int topk_run(const float* q, const float* db, int64_t n_q, int64_t n_db, 
   topk_merge_rescore_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, st>>>(q, db, n_q, n_db, k, L.n_segments, part_s, part_i, margin,
                                                                                out_s, reinterpret_cast<long long*>(out_idx), flagged_rows,
                                                                                flagged_tau, flags);
-  topk_fallback_scan_kernel<<<device_sm_count() * 8, 256, 0, st>>>(q, db, n_db, flagged_rows, flagged_tau, flags, bucket_cnt, bucket_s,
-                                                                   bucket_i, flags);
-  topk_fallback_rank_kernel<<<device_sm_count() * 2, 128, 0, st>>>(k, flagged_rows, flags, bucket_cnt, bucket_s, bucket_i, out_s,
-                                                                   reinterpret_cast<long long*>(out_idx));
+  // Exact fallback for the flagged rows, kTopKBatch at a time. The number of flagged rows is only known on the device, so
+  // every possible batch is launched and the blocks of a batch past the count exit at once (no host synchronisation; a
+  // batch with nothing to do costs two empty launches).
+  const long long batch_rows = std::min<long long>(n_q, kTopKBatch);
+  for (long long b0 = 0; b0 < n_q; b0 += kTopKBatch) {
+    topk_fill_kernel<<<device_sm_count() * 4, 256, 0, st>>>(fb_i, batch_rows * kTopKSlices * kTopKMaxK, -1, flags, b0);
+    topk_fallback_scan_kernel<<<dim3(kTopKSlices, (unsigned)std::min<long long>(batch_rows, 2 * device_sm_count())), 256, 0, st>>>(
+        q, db, n_db, k, b0, flagged_rows, flagged_tau, flags, fb_s, fb_i);
+    topk_fallback_rank_kernel<<<(unsigned)std::min<long long>(batch_rows, 2 * device_sm_count()), 128, 0, st>>>(
+        k, b0, flagged_rows, flags, fb_s, fb_i, out_s, reinterpret_cast<long long*>(out_idx));
+  }
   if (ck(cudaMemcpyAsync(flags_out, flags, 16, cudaMemcpyDeviceToDevice, st), "copy flags") || ck(cudaGetLastError(), "top-k kernels")) return 1;
   return 0;
 }

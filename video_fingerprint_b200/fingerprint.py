@@ -49,44 +49,66 @@ def screen_margin(q: torch.Tensor, db: torch.Tensor) -> float:
     return _BF16_DOT_BOUND * nq * nd * 1.02 + 1e-6
 
 
+_MAX_CANDIDATES = 1 << 26  # screen candidates buffered per native call (12 bytes each); larger joins are split by query rows
+
+
 def threshold_join_device(
     db: torch.Tensor, thr: float, q: Optional[torch.Tensor] = None, q_row0: int = 0, capacity: Optional[int] = None
 ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """All (i, j, s) with <q_i, db_j> >= thr (fp32), as device tensors in no particular order.
-    i is offset by q_row0 (global row index of a row-block shard). Retries with a larger buffer on overflow."""
+    i is offset by q_row0 (global row index of a row-block shard). Retries with a larger buffer on overflow; when a
+    low threshold or a heavily duplicated corpus produces more candidates than `_MAX_CANDIDATES`, the query rows are
+    split into blocks (the reference degrades the same way, one row at a time, fingerprint.py:497-499)."""
     lib = _native.load()
     db = _as_device_f32(db)
     q = db if q is None else _as_device_f32(q, db.device)
     if db.dim() != 2 or db.shape[1] != EMBED_DIM or q.shape[1] != EMBED_DIM:
         raise ValueError("embeddings must be (n, 256)")
-    n_q, n_db = q.shape[0], db.shape[0]
-    dev = db.device
     margin = screen_margin(q, db)
-    cap = int(capacity) if capacity else max(4096, 8 * n_q)
-    cand_cap = 4 * cap
-    with torch.cuda.device(dev):
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        while True:
-            ws = torch.empty(lib.vfp_join_workspace_bytes(n_q, n_db, cand_cap), dtype=torch.uint8, device=dev)
-            out_i = torch.empty(cap, dtype=torch.int32, device=dev)
-            out_j = torch.empty(cap, dtype=torch.int32, device=dev)
-            out_s = torch.empty(cap, dtype=torch.float32, device=dev)
-            counts = torch.zeros(2, dtype=torch.int64, device=dev)
-            rc = lib.vfp_join_threshold(
-                C.c_void_p(q.data_ptr()), C.c_void_p(db.data_ptr()), n_q, n_db, EMBED_DIM, int(q_row0), float(thr), float(margin),
-                C.c_void_p(out_i.data_ptr()), C.c_void_p(out_j.data_ptr()), C.c_void_p(out_s.data_ptr()), cap,
-                C.c_void_p(counts.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(stream),
-            )
-            _native.check(rc, "vfp_join_threshold")
-            n_out, n_cand = (int(v) for v in counts.tolist())
-            if n_cand > cand_cap:  # screen overflow: the candidate count is now known, go again
-                cand_cap = n_cand + 1024
-                cap = max(cap, min(n_cand, 4 * cap))
-                continue
-            if n_out > cap:
-                cap = n_out + 1024
-                continue
-            return out_i[:n_out], out_j[:n_out], out_s[:n_out]
+    dev = db.device
+
+    def run(qb: torch.Tensor, row0: int, cap: int):
+        n_q, n_db = qb.shape[0], db.shape[0]
+        cand_cap = min(4 * cap, _MAX_CANDIDATES)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            while True:
+                ws = torch.empty(lib.vfp_join_workspace_bytes(n_q, n_db, cand_cap), dtype=torch.uint8, device=dev)
+                out_i = torch.empty(cap, dtype=torch.int32, device=dev)
+                out_j = torch.empty(cap, dtype=torch.int32, device=dev)
+                out_s = torch.empty(cap, dtype=torch.float32, device=dev)
+                counts = torch.zeros(2, dtype=torch.int64, device=dev)
+                rc = lib.vfp_join_threshold(
+                    C.c_void_p(qb.data_ptr()), C.c_void_p(db.data_ptr()), n_q, n_db, EMBED_DIM, int(row0), float(thr), float(margin),
+                    C.c_void_p(out_i.data_ptr()), C.c_void_p(out_j.data_ptr()), C.c_void_p(out_s.data_ptr()), cap,
+                    C.c_void_p(counts.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(stream),
+                )
+                _native.check(rc, "vfp_join_threshold")
+                n_out, n_cand = (int(v) for v in counts.tolist())
+                if n_cand > cand_cap:  # screen overflow: the candidate count is now known
+                    if n_cand + 1024 > _MAX_CANDIDATES and n_q > 1:
+                        return None  # too many for one call: the caller splits the query block
+                    cand_cap = n_cand + 1024
+                    cap = max(cap, min(n_cand, 4 * cap))
+                    continue
+                if n_out > cap:
+                    cap = n_out + 1024
+                    continue
+                return out_i[:n_out], out_j[:n_out], out_s[:n_out]
+
+    def solve(lo: int, hi: int, cap: int):
+        # self joins pass the SAME tensor for q and db when the block is the whole matrix (the library then converts it once)
+        qb = q if (lo == 0 and hi == q.shape[0]) else q[lo:hi]
+        out = run(qb, q_row0 + lo, cap)
+        if out is not None:
+            return [out]
+        mid = (lo + hi) // 2
+        return solve(lo, mid, cap) + solve(mid, hi, cap)
+
+    parts = solve(0, q.shape[0], int(capacity) if capacity else max(4096, 8 * q.shape[0]))
+    if len(parts) == 1:
+        return parts[0]
+    return tuple(torch.cat([p[c] for p in parts]) for c in range(3))
 
 
 def threshold_join(db, thr: float, q=None, q_row0: int = 0) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -121,12 +143,10 @@ def topk_inner_product_device(q, db, k: int) -> Tuple[torch.Tensor, torch.Tensor
             ws.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream),
         )
         _native.check(rc, "vfp_topk_ip")
-        if int(flags[1]) != 0:
-            raise _native.NativeError("vfp_topk_ip: exact fallback bucket overflow (too many tied scores)")
     return S, I
 
 
-def preprocess_frames_device(frames) -> torch.Tensor:
+def preprocess_frames_device(frames, device=None) -> torch.Tensor:
     """Device restatement of ``_preprocess_frames`` (fingerprint.py:186-214) up to, not including, the ``/ 255`` and the
     HWC->CHW permute (both are fused into the stem kernel): decoded frames ``(T, H, W, 3)`` uint8 (a tensor, an array or a
     list of equally sized arrays) -> ``(T, 64, 64, 3)`` uint8 on the device, bit-exact with cv2.resize(INTER_AREA) +
@@ -140,7 +160,7 @@ def preprocess_frames_device(frames) -> torch.Tensor:
     if frames.dtype != torch.uint8 or frames.dim() != 4 or frames.shape[3] != 3:
         raise ValueError("frames must be uint8 (T, H, W, 3)")
     if not frames.is_cuda:
-        frames = frames.cuda()
+        frames = frames.cuda(device) if device is not None else frames.cuda()
     frames = frames.contiguous()
     t, h, w, _ = frames.shape
     dev = frames.device
@@ -183,14 +203,17 @@ def group_pairs_topk(S: np.ndarray, I: np.ndarray, thr: float) -> List[List[Tupl
     """fingerprint.py:530-546: each unprocessed row claims its unprocessed top-k neighbours above thr."""
     n = S.shape[0]
     processed = np.zeros(max(n, int(I.max()) + 1 if I.size else n), dtype=bool)
-    hit_rows = np.nonzero((S >= thr).sum(axis=1) > 0)[0]
+    # the reference compares np.float32 scores with the Python float threshold (fingerprint.py:540), which NumPy 2
+    # evaluates in float32: np.float32(0.95) >= 0.95 is True there. One mask, computed once, keeps exactly that rule.
+    above = np.asarray(S, dtype=np.float32) >= np.float32(thr)
+    hit_rows = np.nonzero(above.any(axis=1))[0]
     groups: List[List[Tuple[int, float]]] = []
     for r in hit_rows.tolist():
         if processed[r]:
             continue
         g = []
-        for sim, idx in zip(S[r].tolist(), I[r].tolist()):
-            if sim >= thr and not processed[idx]:
+        for sim, idx, ok in zip(S[r].tolist(), I[r].tolist(), above[r].tolist()):
+            if ok and not processed[idx]:
                 processed[idx] = True
                 g.append((int(idx), float(sim)))
         if len(g) > 1:
@@ -207,6 +230,10 @@ class VideoFingerprintScanner:
     def __init__(self, model_path: Optional[str] = None, device: str = "cuda", batch_size: int = 1, model=None, config: Optional[dict] = None):
         _native.require_cuda()  # the reference silently falls back to CPU (fingerprint.py:27); this build refuses
         self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _native.NativeError(f"device {device!r}: video_fingerprint_b200 runs on CUDA devices only (no CPU fallback)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.batch_size = batch_size
         if model is not None:
             self.model, self.config = model, dict(config or {})
@@ -248,9 +275,12 @@ class VideoFingerprintScanner:
     def extract_fingerprint_from_decoded(self, frames) -> Optional[np.ndarray]:
         """Decoded frames of one video -> embedding: preprocessing and forward both on the device (fingerprint.py:232-270
         minus the PyAV decode). Fewer than 10 frames -> None like the reference (fingerprint.py:238-240)."""
-        if len(frames) < 10:
+        keep = self.subsample(len(frames))            # fingerprint.py:90-101: every skip-th frame, at most max_frames
+        if len(keep) < 10:
             return None
-        u8 = preprocess_frames_device(frames)
+        if len(keep) != len(frames):
+            frames = frames[keep] if isinstance(frames, (np.ndarray, torch.Tensor)) else [frames[i] for i in keep]
+        u8 = preprocess_frames_device(frames, self.device)
         emb = self.model.fingerprint_packed(u8, [u8.shape[0]])
         return emb[0].cpu().numpy()
 
@@ -292,7 +322,7 @@ class VideoFingerprintScanner:
                 print(f"Video too short: clip {i} ({c.shape[0]} frames)")
         result: List[Optional[np.ndarray]] = [None] * len(clips)
         if keep:
-            emb = self.model.fingerprint_clips([clips[i][: self.max_frames] for i in keep]).cpu().numpy()
+            emb = self.model.fingerprint_clips([clips[i][: self.max_frames].to(self.device) for i in keep]).cpu().numpy()
             for row, i in enumerate(keep):
                 result[i] = emb[row]
         return result
@@ -327,12 +357,13 @@ class VideoFingerprintScanner:
         return out
 
     def _find_duplicates_direct(self, embeddings, paths, fingerprints, threshold) -> List[List[dict]]:
-        pi, pj, ps = threshold_join(embeddings, threshold)
+        pi, pj, ps = threshold_join(_as_device_f32(embeddings, getattr(self, "device", None)), threshold)
         return self._materialise(group_pairs_direct(len(embeddings), pi, pj, ps), paths, fingerprints)
 
     def _find_duplicates_faiss(self, embeddings, paths, fingerprints, threshold) -> List[List[dict]]:
         k = min(20, len(embeddings))
-        S, I = topk_inner_product(embeddings, embeddings, k)
+        E = _as_device_f32(embeddings, getattr(self, "device", None))
+        S, I = topk_inner_product(E, E, k)
         return self._materialise(group_pairs_topk(S, I, threshold), paths, fingerprints)
 
     # -- JSON output (fingerprint.py:550-577; the reference crashes on np.float32 / ndarray members) -

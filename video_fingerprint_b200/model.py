@@ -108,6 +108,7 @@ class VideoFingerprintAttention(nn.Module):
         self.pipelines = 2
         self._native: dict = {}          # device index -> (weights handle, key): one native handle per GPU
         self._workspaces: dict = {}      # device index -> uint8 tensor
+        self._upload: dict = {}          # fingerprint_host: (device, dtype, frame shape) -> (two device buffers, copy stream)
 
     # ------------------------------------------------------------------ native weight handle
     def _weights_key(self) -> tuple:
@@ -170,8 +171,9 @@ class VideoFingerprintAttention(nn.Module):
         hwc = frames.dim() == 4 and tuple(frames.shape[1:]) == (64, 64, 3) and frames.dtype == torch.uint8
         if frames.dim() != 4 or not (hwc or tuple(frames.shape[1:]) == (3, 64, 64)) or frames.shape[0] != total:
             raise ValueError(f"frames must be (sum(lengths)={total}, 3, 64, 64) or uint8 (.., 64, 64, 3), got {tuple(frames.shape)}")
-        if not frames.is_cuda:
-            frames = frames.cuda()
+        if not frames.is_cuda:  # host frames: chunked, double-buffered upload overlapped with the forward (fingerprint.py:246-249)
+            out = self.fingerprint_host(frames, lengths, return_features=return_features)
+            return out
         if hwc:
             code = _native.FRAME_U8_HWC  # decoder layout: /255 and HWC->CHW (fingerprint.py:210-212) happen in conv1's loader
         elif frames.dtype == torch.uint8:
@@ -194,17 +196,82 @@ class VideoFingerprintAttention(nn.Module):
                 acc += t
             cu[n] = acc
             pass_frames = max(min(total, self.frames_per_pass), max(lengths))
-            slices = max(1, min(int(self.pipelines), -(-total // pass_frames)))   # one workspace slice per pass in flight
+            slices = max(1, min(int(self.pipelines), 4, -(-total // pass_frames)))   # one workspace slice per pass in flight
             ws = self._get_workspace(slices * (lib.vfp_forward_workspace_bytes(pass_frames, min(pass_frames, n)) + 1024), dev)
             emb = torch.empty((n, self.embedding_dim), dtype=torch.float32, device=dev)
             feats = torch.empty((total, 256), dtype=torch.float32, device=dev) if return_features else None
             stream = torch.cuda.current_stream(dev).cuda_stream
+            lib.vfp_set_tuning(9, slices)   # passes in flight = workspace slices (library-wide setting, re-stated per call)
             rc = lib.vfp_forward(
                 C.c_void_p(weights), C.c_void_p(frames.data_ptr()), code, C.cast(cu, C.c_void_p), n,
                 C.c_void_p(emb.data_ptr()), C.c_void_p(feats.data_ptr() if feats is not None else None),
                 C.c_void_p(ws.data_ptr()), ws.numel(), C.c_void_p(stream),
             )
             _native.check(rc, "vfp_forward")
+        return (emb, feats) if return_features else emb
+
+    @torch.no_grad()
+    def fingerprint_host(self, frames: torch.Tensor, lengths: Sequence[int], chunk_frames: int = 32768, device=None,
+                         out: Optional[torch.Tensor] = None, return_features: bool = False):
+        """Host-resident frames -> embeddings, the scanner's `clip.to(device); model(clip)` (fingerprint.py:246-249) for a
+        whole corpus: `frames` is a HOST tensor (pinned memory gives asynchronous copies) laid out like `fingerprint_packed`
+        expects. Clips are grouped into chunks of about `chunk_frames` frames; chunk i+1 is uploaded on a copy stream into
+        the second of two device buffers while chunk i runs through the network, so the PCIe transfer and the forward
+        overlap. Returns the (n, D) embeddings on the device, or - when `out` (a host tensor, ideally pinned) is given -
+        copies them into it, synchronises and returns `out`."""
+        _native.require_cuda()
+        if frames.is_cuda:
+            raise ValueError("fingerprint_host takes host frames; use fingerprint_packed for device tensors")
+        lengths = [int(t) for t in lengths]
+        n, total = len(lengths), sum(lengths)
+        if frames.dim() != 4 or frames.shape[0] != total:
+            raise ValueError(f"frames must be (sum(lengths)={total}, ...), got {tuple(frames.shape)}")
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        frames = frames.contiguous()
+        # chunk boundaries on clip boundaries
+        chunks, c0, f0 = [], 0, 0
+        while c0 < n:
+            c1, f1 = c0, f0
+            while c1 < n and (c1 == c0 or f1 - f0 + lengths[c1] <= chunk_frames):
+                f1 += lengths[c1]
+                c1 += 1
+            chunks.append((c0, c1, f0, f1))
+            c0, f0 = c1, f1
+        cap = max(f1 - f0 for _, _, f0, f1 in chunks)
+        key = (dev.index, frames.dtype, tuple(frames.shape[1:]))
+        state = self._upload.get(key)
+        if state is None or state[0][0].shape[0] < cap:
+            bufs = [torch.empty((cap,) + tuple(frames.shape[1:]), dtype=frames.dtype, device=dev) for _ in range(2)]
+            state = (bufs, torch.cuda.Stream(dev))
+            self._upload = {key: state}   # one cached pair: the buffers are as large as a chunk
+        bufs, copy_stream = state
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            emb = torch.empty((n, self.embedding_dim), dtype=torch.float32, device=dev)
+            feats = torch.empty((total, 256), dtype=torch.float32, device=dev) if return_features else None
+            ready = [torch.cuda.Event(), torch.cuda.Event()]
+            free = [torch.cuda.Event(), torch.cuda.Event()]
+            for ev in free:
+                ev.record(main)
+            for i, (a, b, fa, fb) in enumerate(chunks):
+                k = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(free[k])   # the forward that last read this buffer has finished
+                    bufs[k][: fb - fa].copy_(frames[fa:fb], non_blocking=True)
+                    ready[k].record(copy_stream)
+                main.wait_event(ready[k])
+                res = self.fingerprint_packed(bufs[k][: fb - fa], lengths[a:b], return_features=return_features)
+                if return_features:
+                    emb[a:b], feats[fa:fb] = res
+                else:
+                    emb[a:b] = res
+                free[k].record(main)
+            if out is not None:
+                out.copy_(emb, non_blocking=True)
+                main.synchronize()
+                return (out, feats) if return_features else out
         return (emb, feats) if return_features else emb
 
     def fingerprint_clips(self, clips: Sequence[torch.Tensor]) -> torch.Tensor:

@@ -4,8 +4,9 @@ follows:
 
 * forward: clips are independent units -> length-balanced (LPT) partition over ranks, weights replicated,
   NO collective while fingerprinting;
-* join: ONE all-gather of the (n_r, 256) fp32 embedding shards, after which every rank owns the full matrix
-  and joins its contiguous row block against all columns (`q_row0` makes the pair indices global);
+* join: ONE all-gather of the (n_r, 256) fp32 embedding shards, started first and overlapped with the join of the
+  rank's rows against its OWN columns; the other column ranges follow once the gather has landed (`q_row0` and a column
+  offset make the pair indices global);
 * top-k: queries are sharded the same way, the database is the all-gathered matrix -> no merge step;
 * the greedy grouping is sequential in the seed index by definition, so the per-rank pair lists are gathered
   and grouped on rank 0 (host).
@@ -83,18 +84,46 @@ def sharded_fingerprint(model, clips: Sequence[torch.Tensor], group=None) -> tor
     return out
 
 
-def sharded_threshold_join(
-    local_embeddings: torch.Tensor,
-    thr: float,
-    group=None,
-    join_fn: Optional[Callable] = None,
-    gather_to: Optional[int] = 0,
-) -> Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
-    """Row-block sharded all-pairs join. `local_embeddings` is this rank's (n_r, 256) shard of the embedding
-    matrix, shards being consecutive in rank order. One all-gather, then each rank joins rows
-    [row0, row0+n_r) x all columns. Returns the (i, j, s) lists sorted by (i, j) on rank `gather_to`
-    (None elsewhere), or on every rank if gather_to is None.
-    `join_fn(db, thr, q, q_row0) -> (i, j, s)` defaults to the device join; the CPU tests inject the oracle."""
+class _RowGather:
+    """An all-gather of row shards in flight (NCCL runs it on its own stream): `wait()` returns (rows in rank order, counts)."""
+
+    def __init__(self, local: torch.Tensor, group=None):
+        world, _ = _world(group)
+        self.local, self.world, self.work, self.buf = local, world, None, None
+        if world == 1:
+            self.counts = [local.shape[0]]
+            return
+        counts_t = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        all_counts = [torch.zeros_like(counts_t) for _ in range(world)]
+        dist.all_gather(all_counts, counts_t, group=group)
+        self.counts = [int(c.item()) for c in all_counts]
+        self.width = max(self.counts)
+        if local.shape[0] == self.width:
+            padded = local
+        else:
+            padded = torch.zeros((self.width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+            padded[: local.shape[0]] = local
+        self.buf = torch.empty((world * self.width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        self.work = dist.all_gather_into_tensor(self.buf, padded, group=group, async_op=True)
+
+    def wait(self) -> Tuple[torch.Tensor, List[int]]:
+        if self.world == 1:
+            return self.local, self.counts
+        self.work.wait()
+        if all(c == self.width for c in self.counts):
+            return self.buf, self.counts
+        parts = [self.buf[r * self.width : r * self.width + self.counts[r]] for r in range(self.world)]
+        return torch.cat(parts, dim=0), self.counts
+
+
+def sharded_threshold_join_device(
+    local_embeddings: torch.Tensor, thr: float, group=None, join_fn: Optional[Callable] = None
+) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, int]:
+    """Row-block sharded all-pairs join, device part. `local_embeddings` is this rank's (n_r, 256) shard, shards being
+    consecutive in rank order. The all-gather of the shards is started first and runs (NCCL, NVLink) WHILE the rank joins
+    its rows against its own columns - the one block that needs no remote data; the two remaining column ranges follow
+    when the gather has landed. Returns this rank's (i, j, s) with GLOBAL indices (device tensors, unordered) and the
+    total row count. `join_fn(db, thr, q, q_row0) -> (i, j, s)` defaults to the device join; the CPU tests inject the oracle."""
     world, rank = _world(group)
     if join_fn is None:
         from .fingerprint import threshold_join_device
@@ -102,21 +131,50 @@ def sharded_threshold_join(
         def join_fn(db, thr_, q, q_row0):  # noqa: E306
             return threshold_join_device(db, thr_, q=q, q_row0=q_row0)
 
-    full, counts = all_gather_rows(local_embeddings.float().contiguous(), group)
-    row0 = sum(counts[:rank])
-    if local_embeddings.shape[0] > 0:
-        i, j, s = join_fn(full, thr, local_embeddings.float().contiguous(), row0)
-        i, j, s = torch.as_tensor(i), torch.as_tensor(j), torch.as_tensor(s)
-    else:
-        i = j = torch.zeros(0, dtype=torch.int64)
-        s = torch.zeros(0, dtype=torch.float32)
-    trip = torch.stack([i.to(torch.float64), j.to(torch.float64), s.to(torch.float64)], dim=1).to(full.device)
+    local = local_embeddings.float().contiguous()
+    gather = _RowGather(local, group)
+    row0 = sum(gather.counts[:rank])
+    n_loc, n_all = local.shape[0], sum(gather.counts)
+    out = []
+
+    def block(db, col0):
+        if n_loc == 0 or db.shape[0] == 0:
+            return
+        i, j, s = (torch.as_tensor(t) for t in join_fn(db, thr, local, row0))
+        out.append((i.to(torch.int64), j.to(torch.int64) + col0, s.to(torch.float32)))
+
+    block(local, row0)                       # own columns: overlaps the gather
+    full, _ = gather.wait()
+    if world > 1:
+        block(full[:row0], 0)
+        block(full[row0 + n_loc :], row0 + n_loc)
+    if not out:
+        z = torch.zeros(0, dtype=torch.int64, device=local.device)
+        return z, z.clone(), torch.zeros(0, dtype=torch.float32, device=local.device), n_all
+    return torch.cat([o[0] for o in out]), torch.cat([o[1] for o in out]), torch.cat([o[2] for o in out]), n_all
+
+
+def sharded_threshold_join(
+    local_embeddings: torch.Tensor,
+    thr: float,
+    group=None,
+    join_fn: Optional[Callable] = None,
+    gather_to: Optional[int] = 0,
+) -> Optional[Tuple[np.ndarray, np.ndarray, np.ndarray]]:
+    """`sharded_threshold_join_device` + the gather of the per-rank pair lists (as int32, int32, fp32 bits - 12 bytes a
+    pair) for the sequential greedy grouping. Returns (i, j, s) sorted by (i, j) on rank `gather_to` (None elsewhere), or
+    on every rank if gather_to is None."""
+    world, rank = _world(group)
+    i, j, s, _ = sharded_threshold_join_device(local_embeddings, thr, group, join_fn)
+    dev = local_embeddings.device
+    trip = torch.stack([i.to(torch.int32), j.to(torch.int32), s.contiguous().view(torch.int32)], dim=1).to(dev)
     if world > 1:
         trip, _ = all_gather_rows(trip, group)
     if gather_to is not None and rank != gather_to:
         return None
-    t = trip.cpu().numpy()
-    pi, pj, ps = t[:, 0].astype(np.int64), t[:, 1].astype(np.int64), t[:, 2].astype(np.float32)
+    t = trip.cpu()
+    pi, pj = t[:, 0].numpy().astype(np.int64), t[:, 1].numpy().astype(np.int64)
+    ps = t[:, 2].contiguous().view(torch.float32).numpy()
     order = np.lexsort((pj, pi))
     return pi[order], pj[order], ps[order]
 
