@@ -13,7 +13,7 @@ import video_fingerprint_b200 as vfp
 from oracle import join_oracle
 from oracle.weights import make_state_dict, state_dict_digest, state_spec
 from video_fingerprint_b200 import _native, fingerprint
-from video_fingerprint_b200.sharding import partition_clips, row_block
+from video_fingerprint_b200.sharding import partition_clips, row_block, symmetric_block_plan
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -139,3 +139,21 @@ def test_topk_grouping_compares_in_float32_like_the_reference():
     pi, pj = np.array([0, 0, 1, 1]), np.array([0, 1, 0, 1])
     ps = np.array([1.0, edge, edge, 1.0], dtype=np.float32)
     assert [[i for i, _ in g] for g in fingerprint.group_pairs_direct(2, pi, pj, ps)] == [[0, 1]]
+
+
+@pytest.mark.parametrize("counts", [[5], [4, 3], [3, 4, 2], [5, 5, 4, 6], [3, 1, 4, 1, 5], [2, 3, 2, 3, 2, 3, 2, 3], [4, 0, 3, 5]])
+def test_symmetric_block_plan_covers_every_ordered_pair_once(counts):
+    """Sharded join: each block of the symmetric score matrix is computed by one rank and mirrored. Element-level check that
+    diagonal blocks + (off-diagonal blocks and their mirror images) tile the n x n matrix exactly once."""
+    world, n = len(counts), sum(counts)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    cover = np.zeros((n, n), dtype=int)
+    for rank in range(world):
+        plan = symmetric_block_plan(world, rank, counts)
+        q_lo, q_hi, c_lo, c_hi = plan[0]
+        assert (q_lo, q_hi, c_lo, c_hi) == (0, counts[rank], starts[rank], starts[rank + 1])
+        cover[starts[rank] : starts[rank + 1], starts[rank] : starts[rank + 1]] += 1
+        for q_lo, q_hi, c_lo, c_hi in plan[1:]:
+            cover[starts[rank] + q_lo : starts[rank] + q_hi, c_lo:c_hi] += 1
+            cover[c_lo:c_hi, starts[rank] + q_lo : starts[rank] + q_hi] += 1     # the mirrored pairs
+    assert np.all(cover == 1)

@@ -345,12 +345,14 @@ struct EpiJoinThreshold : EpiDefaults {
     float* out_s;
     unsigned long long* count;
     long long capacity;
+    int tri;                    // self join: keep j >= i only (the mirrored pair is emitted by the re-score kernel)
   };
   __device__ __forceinline__ void begin(const Params&, int, int, int) {}
   __device__ __forceinline__ void end(const Params&, int, int, int) {}
   __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int /*pass*/) {
     const long long qi = (long long)mt * 128 + row;
     if (qi >= p.q_rows) return;
+    if (p.tri && (long long)col0 + 31 < qi) return;   // the whole chunk lies below the diagonal
     float m = __uint_as_float(v[0]);
 #pragma unroll
     for (int i = 1; i < 32; ++i) m = fmaxf(m, __uint_as_float(v[i]));
@@ -359,7 +361,7 @@ struct EpiJoinThreshold : EpiDefaults {
     for (int i = 0; i < 32; ++i) {
       const float s = __uint_as_float(v[i]);
       const long long j = (long long)col0 + i;
-      if (s >= p.thr && j < p.db_rows) {
+      if (s >= p.thr && j < p.db_rows && (!p.tri || j >= qi)) {
         const unsigned long long slot = atomicAdd(p.count, 1ull);
         if ((long long)slot < p.capacity) {
           p.out_i[slot] = (int)(p.q_row0 + qi);

@@ -62,12 +62,15 @@ inline cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
   return e;
 }
 
-// Programmatic dependent launch (vfp_set_tuning key 7, default on): every kernel of the forward chain executes
+// Programmatic dependent launch (vfp_set_tuning key 7): every kernel of the forward chain executes
 // griddepcontrol.launch_dependents at its top and griddepcontrol.wait before it touches memory, so the next
 // kernel's CTAs are scheduled - and run their prologue (barrier init, TMEM allocation, descriptor prefetch) - while
 // the tail of the current kernel drains. Kernels launched this way MUST call pdl_wait() (sm100_primitives.cuh).
+// OFF by default: measured on B200 over 10 000 x 64-frame clips it changes nothing or costs up to 2 % (39.2-39.9 ms per
+// step with it, 38.6-38.9 without, profiles/r02_ab_schedule.txt) - the forward is 160 long launches per step, their
+// tails are not where the time goes.
 inline std::atomic<int>& pdl_enabled() {
-  static std::atomic<int> v{1};
+  static std::atomic<int> v{0};
   return v;
 }
 
@@ -114,6 +117,20 @@ inline cudaError_t launch_gemm_bres(const CUtensorMap& ta, const CUtensorMap& tb
   if (total <= 0) return cudaSuccess;
   const int grid = total < persistent_grid() ? (int)total : persistent_grid();
   return launch_kernel(kernel, dim3(grid), dim3(gemm_threads<BLOCK_N, Epi>()), kSmem, stream, ta, tb, shape, ep);
+}
+
+template <int STAGES, class Epi>
+inline cudaError_t launch_gemm_ares(const CUtensorMap& ta, const CUtensorMap& tb, const AresShape& shape,
+                                    const typename Epi::Params& ep, cudaStream_t stream) {
+  using L = AresSmemLayout<STAGES>;
+  constexpr int kSmem = L::kTotal + Epi::kExtraSmemBytes;
+  static_assert(kSmem <= 232448, "shared memory budget");
+  auto kernel = gemm_ares_tcgen05_kernel<STAGES, Epi>;
+  if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), kSmem); e != cudaSuccess) return e;
+  const long long total = (long long)shape.m_super * shape.n_panels;
+  if (total <= 0) return cudaSuccess;
+  const int grid = total < persistent_grid() ? (int)total : persistent_grid();
+  return launch_kernel(kernel, dim3(grid), dim3(gemm_threads<kAresBlockN, Epi>()), kSmem, stream, ta, tb, shape, ep);
 }
 
 inline GemmShape plain_shape(long long M, int N, int K, int block_n, int block_k, int group_m = 16) {

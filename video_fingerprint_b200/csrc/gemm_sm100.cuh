@@ -514,4 +514,223 @@ gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   }
 }
 
+// =================================================================================================
+// A-resident, panel-major variant for the all-pairs similarity join (vfp_join_threshold).
+// The plain kernel above re-fetches BOTH operands for every 128 x 256 tile: 192 KB per 2 048 MMA cycles = 94 B/clk per SM,
+// above what L2 -> SM delivers, so the join ran at 0.59-0.75 of the tensor peak. Here a work item is
+//      (a super-tile of kAresMT x 128 query rows) x (one PANEL of database column tiles),
+// the query super-tile (all four K blocks, 128 KB) is loaded ONCE per item and stays in shared memory, and only the
+// database streams through the ring in 128-row x 64-column blocks: 64 KB per 2 048 MMA cycles = 32 B/clk. UMMAs are
+// M128 N128 K16 (64 cycles each, the tensor pipe's full rate), two independent accumulators per column tile (one per
+// query sub-tile), TMEM double buffered: 2 x 2 x 128 = 512 columns.
+// Items are numbered PANEL-MAJOR and dealt round-robin, so at any time all CTAs work inside the same one or two panels:
+// a panel (<= 65 536 database rows = 32 MB of bf16) is read from HBM once and then served from L2 however far the CTAs
+// drift apart; a row-major order would let 148 CTAs stream 148 different parts of a database that does not fit L2.
+// `tri` (self joins): S is symmetric, so column tiles that lie entirely below the diagonal of the item's rows are
+// skipped; the epilogue keeps j >= i and the re-score kernel emits the mirrored pair.
+// =================================================================================================
+constexpr int kAresMT = 2;
+constexpr int kAresBlockN = 128;
+constexpr int kAresKB = 4;   // K = 256 = 4 blocks of 64
+
+struct AresShape {
+  int m_super;        // super-tiles of kAresMT * 128 query rows
+  int n_tiles;        // database column tiles of 128 rows
+  int panel_tiles;    // column tiles per panel
+  int n_panels;
+  int tri;            // 1: skip column tiles strictly below the diagonal
+  long long q_row0;   // global index of query row 0 (position of the diagonal)
+};
+
+struct AresWalk {
+  const AresShape& s;
+  long long cur, stride, limit;
+  __device__ AresWalk(const AresShape& shape, int cta, int n_cta)
+      : s(shape), cur(cta), stride(n_cta), limit((long long)shape.m_super * shape.n_panels) {}
+  // next non-empty item of this CTA: super-tile index and its column tile range [nt0, nt1)
+  __device__ bool next(int& mts, int& nt0, int& nt1) {
+    while (cur < limit) {
+      const int p = (int)(cur / s.m_super);
+      mts = (int)(cur - (long long)p * s.m_super);
+      cur += stride;
+      nt0 = p * s.panel_tiles;
+      nt1 = min(s.n_tiles, nt0 + s.panel_tiles);
+      if (s.tri) nt0 = max(nt0, (int)((s.q_row0 + (long long)mts * (kAresMT * kBlockM)) / kAresBlockN));
+      if (nt0 < nt1) return true;
+    }
+    return false;
+  }
+};
+
+template <int STAGES>
+struct AresSmemLayout {
+  static constexpr int kABytes = kBlockM * 128;                      // one K block of one 128-row sub-tile
+  static constexpr int kAResident = kAresMT * kAresKB * kABytes;     // 128 KB
+  static constexpr int kBBytes = kAresBlockN * 128;                  // one K block of a database tile
+  static constexpr int kCore = kAResident + STAGES * kBBytes + 256;
+  static constexpr int kCoreAligned = (kCore + 1023) / 1024 * 1024;
+  static constexpr int kTotal = kCoreAligned + 1024;
+};
+
+template <int STAGES, class Epilogue>
+__global__ void __launch_bounds__(gemm_threads<kAresBlockN, Epilogue>(), 1)
+gemm_ares_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const AresShape shape, const __grid_constant__ typename Epilogue::Params ep) {
+  using L = AresSmemLayout<STAGES>;
+  constexpr int kAccCols = kAresMT * kAresBlockN;   // 256 columns per accumulator buffer
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + L::kAResident;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kAResident + STAGES * L::kBBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* acc_full = bars + 2 * STAGES;
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;
+  uint64_t* a_full = bars + 2 * STAGES + 4;
+  uint64_t* a_empty = bars + 2 * STAGES + 5;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 4 * gemm_column_split<kAresBlockN, Epilogue>());
+    }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      AresWalk walk(shape, blockIdx.x, gridDim.x);
+      int mts, nt0, nt1;
+      while (walk.next(mts, nt0, nt1)) {
+        mbar_wait(a_empty, a_phase ^ 1);   // the previous item's UMMAs have read the resident query tile
+        a_phase ^= 1;
+        mbar_arrive_expect_tx(a_full, L::kAResident);
+#pragma unroll
+        for (int sub = 0; sub < kAresMT; ++sub)
+#pragma unroll
+          for (int kb = 0; kb < kAresKB; ++kb)
+            tma_load_2d(&tmap_a, a_full, smem_a + (sub * kAresKB + kb) * L::kABytes, kb * 64, (mts * kAresMT + sub) * kBlockM);
+        for (int nt = nt0; nt < nt1; ++nt) {
+#pragma unroll
+          for (int kb = 0; kb < kAresKB; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_arrive_expect_tx(&full_bar[stage], L::kBBytes);
+            tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * L::kBBytes, kb * 64, nt * kAresBlockN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ UMMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, kAresBlockN);
+      int stage = 0, local = 0;
+      uint32_t phase = 0, a_phase = 0;
+      AresWalk walk(shape, blockIdx.x, gridDim.x);
+      int mts, nt0, nt1;
+      const uint32_t a_base = smem_u32(smem_a);
+      while (walk.next(mts, nt0, nt1)) {
+        mbar_wait(a_full, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        for (int nt = nt0; nt < nt1; ++nt, ++local) {
+          const int acc = local & 1;
+          mbar_wait(&acc_empty[acc], ((local >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kAccCols;
+#pragma unroll
+          for (int kb = 0; kb < kAresKB; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t bdesc = umma_smem_desc_kmajor<128>(smem_u32(smem_b + stage * L::kBBytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+#pragma unroll
+              for (int sub = 0; sub < kAresMT; ++sub) {
+                const uint64_t adesc = umma_smem_desc_kmajor<128>(a_base + (sub * kAresKB + kb) * L::kABytes);
+                umma_bf16(d_tmem + sub * kAresBlockN, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
+            }
+            umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit(&acc_full[acc]);
+        }
+        umma_commit(a_empty);   // arrives when every UMMA of this item has completed
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    constexpr int kSplit = gemm_column_split<kAresBlockN, Epilogue>();
+    constexpr int kColsPerWarp = kAresBlockN / kSplit;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
+    int local = 0;
+    AresWalk walk(shape, blockIdx.x, gridDim.x);
+    int mts, nt0, nt1;
+    Epilogue epi;
+    epi.setup(ep, smem + L::kCoreAligned, warp - 2, lane);
+    while (walk.next(mts, nt0, nt1)) {
+      for (int nt = nt0; nt < nt1; ++nt, ++local) {
+        const int acc = local & 1;
+        mbar_wait(&acc_full[acc], (local >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int sub = 0; sub < kAresMT; ++sub) {
+          const int mt = mts * kAresMT + sub;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccCols + sub * kAresBlockN;
+          epi.begin(ep, mt, nt, row);
+#pragma unroll 1
+          for (int c = col_begin; c < col_begin + kColsPerWarp; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c, v);
+            tmem_ld_wait();
+            epi.chunk(ep, mt, nt * kAresBlockN + c, row, v, 0);
+          }
+          epi.end(ep, mt, nt, row);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      }
+    }
+    epi.finish(ep, lane);
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace vfp

@@ -15,7 +15,7 @@ rescore_pairs_kernel(const float* __restrict__ q, const float* __restrict__ db, 
                      const int* __restrict__ cand_i, const int* __restrict__ cand_j,
                      const unsigned long long* __restrict__ cand_count, long long cand_capacity, float thr,
                      int* __restrict__ out_i, int* __restrict__ out_j, float* __restrict__ out_s,
-                     unsigned long long* __restrict__ out_count, long long capacity) {
+                     unsigned long long* __restrict__ out_count, long long capacity, int mirror) {
   const int lane = threadIdx.x & 31;
   const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
   long long n = (long long)*cand_count;
@@ -33,11 +33,19 @@ rescore_pairs_kernel(const float* __restrict__ q, const float* __restrict__ db, 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0 && s >= thr) {
-      const unsigned long long slot = atomicAdd(out_count, 1ull);
+      // mirror (symmetric self join, candidates have j >= i): the pair below the diagonal has the same fp32 score
+      // (the products commute term by term and are summed in the same order)
+      const bool twin = mirror && (long long)gj != (long long)gi - q_row0;
+      const unsigned long long slot = atomicAdd(out_count, twin ? 2ull : 1ull);
       if ((long long)slot < capacity) {
         out_i[slot] = gi;
         out_j[slot] = gj;
         out_s[slot] = s;
+      }
+      if (twin && (long long)slot + 1 < capacity) {
+        out_i[slot + 1] = (int)(gj + q_row0);
+        out_j[slot + 1] = (int)(gi - q_row0);
+        out_s[slot + 1] = s;
       }
     }
   }

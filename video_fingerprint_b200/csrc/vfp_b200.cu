@@ -252,6 +252,9 @@ int64_t g_stem_pass_frames = kConvPassFrames;
 // default for u8 / bf16 frames; vfp_set_tuning(1, 0) selects the two-kernel path (always used for fp32 frames).
 int g_fused_stem = 2;
 int g_join_prefetch = 16;  // vfp_set_tuning key 5: column tiles of L2 prefetch distance in the join (0 = off)
+int g_join_kernel = 1;      // key 10: 1 = A-resident panel-major kernel, 0 = the generic tile kernel
+int g_join_symmetric = 1;   // key 11: self joins screen the upper triangle only
+int g_join_panel_tiles = 512;  // key 12: database column tiles (of 128 rows) per L2 panel
 
 struct TokenWs {
   size_t cu, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, h, logits, xbf, pooled, pooled_bf, head_h, total;
@@ -305,8 +308,10 @@ size_t forward_ws_total(int64_t F, int64_t C) {
 }
 
 // Pipelines of vfp_forward (vfp_set_tuning key 9): token passes are dealt round-robin onto this many internal streams.
+// Measured on B200 (10 000 x 64-frame clips): 1 pipeline 38.6-38.9 ms per step, 2 pipelines 38.6-39.6, 3 pipelines 39.9 -
+// the kernels of one pass already fill the GPU, so the default is ONE pipeline (the caller's stream, no fork / join).
 constexpr int kMaxPipes = 4;
-int g_forward_pipes = 2;
+int g_forward_pipes = 1;
 
 // Internal non-blocking streams, created once per device and shared by all calls (work of different calls on the same
 // pipeline stream simply queues up; the fork / join events are per call).
@@ -347,6 +352,9 @@ int vfp_set_tuning(int key, long long value) {
   if (key == 5 && value >= 0 && value <= 4096) { g_join_prefetch = (int)value; return 0; }
   if (key == 6 && value >= 0 && value <= 4096) { g_topk_prefetch = (int)value; return 0; }
   if (key == 3 && value >= 64 && value <= kConvPassFrames) { g_conv_pass_frames = value; return 0; }
+  if (key == 10 && value >= 0 && value <= 1) { g_join_kernel = (int)value; return 0; }
+  if (key == 11 && value >= 0 && value <= 1) { g_join_symmetric = (int)value; return 0; }
+  if (key == 12 && value >= 16 && value <= 65536) { g_join_panel_tiles = (int)value; return 0; }
   if (key == 7 && value >= 0 && value <= 1) { pdl_enabled().store((int)value); return 0; }            // programmatic dependent launch
   if (key == 8 && value >= 0 && value <= 4096) { persistent_cta_limit().store((int)value); return 0; }  // CTAs per persistent kernel (0 = all SMs)
   if (key == 9 && value >= 1 && value <= kMaxPipes) { g_forward_pipes = (int)value; return 0; }        // pipelines (internal streams) of vfp_forward
@@ -995,22 +1003,44 @@ int vfp_join_threshold(const float* q, const float* db, int64_t n_q, int64_t n_d
   VFP_CUDA(cudaMemsetAsync(counts, 0, 16, st));
   f32_to_bf16_kernel<<<(unsigned)((n_q * 32 + 255) / 256), 256, 0, st>>>(q, qbf, n_q * 32);
   if (!self_join) f32_to_bf16_kernel<<<(unsigned)((n_db * 32 + 255) / 256), 256, 0, st>>>(db, dbbf, n_db * 32);
-  CUtensorMap ta, tb;
-  if (make_tmap_rows_bf16(&ta, qbf, (uint64_t)n_q, 256, 256, 128, 64) ||
-      make_tmap_rows_bf16(&tb, dbbf, (uint64_t)n_db, 256, 256, 256, 64))
-    return fail("vfp_join_threshold: tensor map encode failed");
-  GemmShape s = plain_shape(n_q, 0, 256, 256, 64, 32);
-  s.n_tiles = (int)((n_db + 255) / 256);
-  // L2 prefetch of the database tiles: +22 % at 2 M rows, +14 % at 1 M, but -7 % while the bf16 database (512 B per row)
-  // still fits the 126 MB L2 (262 144 rows), where it is only extra traffic
-  s.b_prefetch_tiles = (size_t)n_db * 512 > ((size_t)160 << 20) ? g_join_prefetch : 0;
+  // a self join's score matrix is symmetric: screen the upper triangle only, the re-score kernel emits both orders
+  const int tri = (self_join && g_join_symmetric) ? 1 : 0;
   EpiJoinThreshold::Params ep{};
   ep.thr = thr - screen_margin;
   ep.q_rows = n_q; ep.db_rows = n_db; ep.q_row0 = q_row0;
   ep.out_i = cand_i; ep.out_j = cand_j; ep.out_s = cand_s; ep.count = cand_count; ep.capacity = cand_cap;
-  VFP_CUDA((launch_gemm<256, 64, 4, EpiJoinThreshold>(ta, tb, s, ep, st)));  // measured faster than the B-resident variant here
+  CUtensorMap ta, tb;
+  if (g_join_kernel == 1) {   // A-resident, panel-major schedule (gemm_sm100.cuh)
+    if (make_tmap_rows_bf16(&ta, qbf, (uint64_t)n_q, 256, 256, 128, 64) ||
+        make_tmap_rows_bf16(&tb, dbbf, (uint64_t)n_db, 256, 256, 128, 64))
+      return fail("vfp_join_threshold: tensor map encode failed");
+    AresShape s{};
+    s.m_super = (int)((n_q + kAresMT * kBlockM - 1) / (kAresMT * kBlockM));
+    s.n_tiles = (int)((n_db + kAresBlockN - 1) / kAresBlockN);
+    // a panel of <= 65 536 database rows (32 MB of bf16) stays in L2 while every query super-tile passes over it; small
+    // problems get shorter panels so that there are enough items to balance the SMs
+    int panel = g_join_panel_tiles;
+    while (panel > 16 && (long long)s.m_super * ((s.n_tiles + panel - 1) / panel) < 16LL * persistent_grid()) panel /= 2;
+    s.panel_tiles = panel;
+    s.n_panels = (s.n_tiles + panel - 1) / panel;
+    s.tri = tri;
+    s.q_row0 = 0;   // tri compares LOCAL row and column indices: q and db are the same matrix
+    ep.tri = tri;
+    VFP_CUDA((launch_gemm_ares<5, EpiJoinThreshold>(ta, tb, s, ep, st)));
+  } else {
+    if (make_tmap_rows_bf16(&ta, qbf, (uint64_t)n_q, 256, 256, 128, 64) ||
+        make_tmap_rows_bf16(&tb, dbbf, (uint64_t)n_db, 256, 256, 256, 64))
+      return fail("vfp_join_threshold: tensor map encode failed");
+    GemmShape s = plain_shape(n_q, 0, 256, 256, 64, 32);
+    s.n_tiles = (int)((n_db + 255) / 256);
+    // L2 prefetch of the database tiles: +22 % at 2 M rows, +14 % at 1 M, but -7 % while the bf16 database (512 B per row)
+    // still fits the 126 MB L2 (262 144 rows), where it is only extra traffic
+    s.b_prefetch_tiles = (size_t)n_db * 512 > ((size_t)160 << 20) ? g_join_prefetch : 0;
+    ep.tri = tri;   // this kernel visits every tile; the epilogue still drops what lies below the diagonal
+    VFP_CUDA((launch_gemm<256, 64, 4, EpiJoinThreshold>(ta, tb, s, ep, st)));
+  }
   rescore_pairs_kernel<<<device_sm_count() * 4, 256, 0, st>>>(q, db, dim, q_row0, cand_i, cand_j, cand_count, cand_cap, thr,
-                                                              out_i, out_j, out_s, counts, capacity);
+                                                              out_i, out_j, out_s, counts, capacity, tri);
   // counts[1] = candidate count (device-side copy so the caller reads both with one transfer)
   VFP_CUDA(cudaMemcpyAsync(counts + 1, cand_count, 8, cudaMemcpyDeviceToDevice, st));
   VFP_CUDA(cudaGetLastError());

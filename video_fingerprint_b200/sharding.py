@@ -84,6 +84,26 @@ def sharded_fingerprint(model, clips: Sequence[torch.Tensor], group=None) -> tor
     return out
 
 
+def symmetric_block_plan(world: int, rank: int, counts: Sequence[int]) -> List[Tuple[int, int, int, int]]:
+    """Blocks of the symmetric score matrix rank `rank` computes, as (local row lo, local row hi, global column lo, global
+    column hi). Entry 0 is the rank's diagonal block (a self join). Every other entry is reported together with its mirror
+    image, so each unordered pair of ranks appears in exactly ONE plan: rank r takes the peers r+1 .. r+(G-1)/2 (cyclically);
+    for even G the block against the opposite rank is split in half between the two."""
+    starts = [sum(counts[:r]) for r in range(world)]
+    n_loc = counts[rank]
+    plan = [(0, n_loc, starts[rank], starts[rank] + n_loc)]
+    for d in range(1, (world - 1) // 2 + 1):
+        peer = (rank + d) % world
+        plan.append((0, n_loc, starts[peer], starts[peer] + counts[peer]))
+    if world > 1 and world % 2 == 0:
+        peer = (rank + world // 2) % world
+        if rank < world // 2:    # my first half of rows x all of the peer's columns
+            plan.append((0, n_loc // 2, starts[peer], starts[peer] + counts[peer]))
+        else:                    # all my rows x the columns of the peer's rows the peer did not take
+            plan.append((0, n_loc, starts[peer] + counts[peer] // 2, starts[peer] + counts[peer]))
+    return plan
+
+
 class _RowGather:
     """An all-gather of row shards in flight (NCCL runs it on its own stream): `wait()` returns (rows in rank order, counts)."""
 
@@ -122,8 +142,10 @@ def sharded_threshold_join_device(
     """Row-block sharded all-pairs join, device part. `local_embeddings` is this rank's (n_r, 256) shard, shards being
     consecutive in rank order. The all-gather of the shards is started first and runs (NCCL, NVLink) WHILE the rank joins
     its rows against its own columns - the one block that needs no remote data; the two remaining column ranges follow
-    when the gather has landed. Returns this rank's (i, j, s) with GLOBAL indices (device tensors, unordered) and the
-    total row count. `join_fn(db, thr, q, q_row0) -> (i, j, s)` defaults to the device join; the CPU tests inject the oracle."""
+    when the gather has landed. The score matrix is symmetric, so every block of it is computed by ONE rank, which also
+    reports the mirrored pairs: the union of the ranks' results is the full ordered pair set, each pair exactly once,
+    but a rank's list is not restricted to its own rows. Returns (i, j, s) with GLOBAL indices (device tensors,
+    unordered) and the total row count. `join_fn(db, thr, q, q_row0) -> (i, j, s)` defaults to the device join; the CPU tests inject the oracle."""
     world, rank = _world(group)
     if join_fn is None:
         from .fingerprint import threshold_join_device
@@ -133,21 +155,25 @@ def sharded_threshold_join_device(
 
     local = local_embeddings.float().contiguous()
     gather = _RowGather(local, group)
-    row0 = sum(gather.counts[:rank])
-    n_loc, n_all = local.shape[0], sum(gather.counts)
+    counts = gather.counts
+    starts = [sum(counts[:r]) for r in range(world)]
+    row0, n_loc, n_all = starts[rank], local.shape[0], sum(counts)
     out = []
 
-    def block(db, col0):
-        if n_loc == 0 or db.shape[0] == 0:
+    def block(db, col0, q=None, q0=0, mirror=False):
+        q = local if q is None else q
+        if q.shape[0] == 0 or db.shape[0] == 0:
             return
-        i, j, s = (torch.as_tensor(t) for t in join_fn(db, thr, local, row0))
-        out.append((i.to(torch.int64), j.to(torch.int64) + col0, s.to(torch.float32)))
+        i, j, s = (torch.as_tensor(t) for t in join_fn(db, thr, q, row0 + q0))
+        i, j, s = i.to(torch.int64), j.to(torch.int64) + col0, s.to(torch.float32)
+        out.append((i, j, s))
+        if mirror:   # S is symmetric: the block (peer rows x my columns) is this one transposed
+            out.append((j, i, s))
 
-    block(local, row0)                       # own columns: overlaps the gather
+    block(local, row0)                       # own columns (a self join: the library screens the upper triangle only); overlaps the gather
     full, _ = gather.wait()
-    if world > 1:
-        block(full[:row0], 0)
-        block(full[row0 + n_loc :], row0 + n_loc)
+    for q_lo, q_hi, c_lo, c_hi in symmetric_block_plan(world, rank, counts)[1:]:
+        block(full[c_lo:c_hi], c_lo, q=None if (q_lo, q_hi) == (0, n_loc) else local[q_lo:q_hi], q0=q_lo, mirror=True)
     if not out:
         z = torch.zeros(0, dtype=torch.int64, device=local.device)
         return z, z.clone(), torch.zeros(0, dtype=torch.float32, device=local.device), n_all
