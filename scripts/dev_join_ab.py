@@ -13,8 +13,8 @@ out = []
 for n in [int(a) for a in sys.argv[1:]] or [262144, 1048576]:
     E = make_join_data(n, dev)
     ref = None
-    for name, tun in [("tile_full", {10: 0, 11: 0}), ("ares_full", {10: 1, 11: 0}), ("ares_tri", {10: 1, 11: 1}), ("tile_tri", {10: 0, 11: 1}),
-                      ("ares_tri_p256", {10: 1, 11: 1, 12: 256}), ("ares_tri_p1024", {10: 1, 11: 1, 12: 1024}), ("ares_full_p1024", {10: 1, 11: 0, 12: 1024})]:
+    for name, tun in [("tile_full", {10: 0, 11: 0}), ("ares_full", {10: 1, 11: 0}), ("ares_tri", {10: 1, 11: 1}),
+                      ("pair_full", {10: 2, 11: 0}), ("pair_tri", {10: 2, 11: 1})]:
         for k, v in {12: 512, **tun}.items():
             assert lib.vfp_set_tuning(k, v) == 0
         i, j, s = vfp.threshold_join_device(E, 0.95)

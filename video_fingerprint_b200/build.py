@@ -43,12 +43,16 @@ def _nvcc() -> str:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= _sources_mtime():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", LIB_PATH, os.path.join(CSRC, "vfp_b200.cu")]
+    tmp = LIB_PATH + ".tmp%d" % os.getpid()   # written aside and renamed: a snapshot of the tree never sees a half-written library
+    cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", tmp, os.path.join(CSRC, "vfp_b200.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB_PATH)
     if verbose:
         print(res.stderr)
     return LIB_PATH

@@ -19,6 +19,37 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, t, hx);
 }
 
+// Two values at once, in half precision. The MLP evaluates 2.6e9 GELUs per 10 000 clips; in fp32 (even as packed FMUL2 / FFMA2)
+// that is ~12 FMA-pipe cycles per element and warp, which made the activation phase - not the tensor pipe - the pace of the
+// fused feed-forward kernel (cycle trace: 4 800 cycles of GELU per 128 x 256 chunk against 4 096 cycles of UMMAs). The result
+// is stored as bf16 (8 mantissa bits), so the polynomial, the tanh and the blend run as fp16x2 instructions (11 bits, one
+// instruction per PAIR): x -> f16x2, u = x (c0 + c1 x^2), t = tanh.approx.f16x2(u), y = 0.5 x t + 0.5 x. Large |x| overflow x^2
+// to inf, which tanh maps to +-1 - the right limit. |fp16 form - fp32 form| < 2^-10 |y| + 2^-11 |x|, below the bf16 rounding of
+// the stored value.
+__device__ __forceinline__ uint32_t gelu_erf2_f16(float2 x) {
+  uint32_t xh, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xh) : "f"(x.y), "f"(x.x));
+  asm("{\n\t"
+      ".reg .b32 x2, p, u, t, hx;\n\t"
+      "mul.rn.f16x2 x2, %1, %1;\n\t"
+      "fma.rn.f16x2 p, x2, %2, %3;\n\t"
+      "mul.rn.f16x2 u, %1, p;\n\t"
+      "tanh.approx.f16x2 t, u;\n\t"
+      "mul.rn.f16x2 hx, %1, %4;\n\t"
+      "fma.rn.f16x2 %0, hx, t, hx;\n\t"
+      "}"
+      : "=r"(y)
+      : "r"(xh), "r"(0x28912891u) /* 0.0356774 */, "r"(0x3A623A62u) /* 0.7978846 */, "r"(0x38003800u) /* 0.5 */);
+  return y;
+}
+// fp32 pair in, fp32 pair out (callers that keep working in fp32)
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  const uint32_t y = gelu_erf2_f16(x);
+  float2 r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}" : "=f"(r.x), "=f"(r.y) : "r"(y));
+  return r;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
@@ -29,6 +60,8 @@ struct EpiDefaults {
   static constexpr int kPasses = 1;
   static constexpr int kColumnSplit = 2;
   static constexpr int kExtraSmemBytes = 0;
+  int block_n_ = 0;   // column tile width of the kernel that runs this epilogue (set once by the kernel)
+  __device__ __forceinline__ void set_block_n(int n) { block_n_ = n; }
   template <class P> __device__ __forceinline__ void setup(const P&, uint8_t*, int, int) {}
   template <class P> __device__ __forceinline__ void finish(const P&, int) {}
   template <class P> __device__ __forceinline__ void item_begin(const P&, int, int, int, uint8_t*) {}
@@ -110,6 +143,28 @@ struct EpiBiasAct : EpiDefaults {
 };
 
 // -------------------------------------------------------------------------------------------
+// Bias of the current column tile in shared memory. These kernels carve ~225 KB of the SM's 228 KB out as shared memory,
+// which leaves no L1: a __ldg of the bias inside the chunk loop is an L2 round trip (300+ cycles) on the epilogue's critical
+// path, eight of them per 32 x 32 chunk (measured on the fused feed-forward kernel: 4.0 -> 3.06 ms when its biases moved
+// to shared memory). All epilogue threads call load() from begin() with the same tile sequence; the tile's <= 256 bias
+// values are (re)loaded only when the column tile changes, between two named barriers of the epilogue threads.
+// -------------------------------------------------------------------------------------------
+struct BiasTileCache {
+  float* s = nullptr;
+  int nt = -1;
+  __device__ __forceinline__ void init(uint8_t* smem_1kb) { s = reinterpret_cast<float*>(smem_1kb); nt = -1; }
+  __device__ __forceinline__ void load(const float* bias, int N, int tile, int block_n) {
+    if (tile == nt || bias == nullptr) return;   // uniform over the epilogue threads
+    const int n_epi = (int)blockDim.x - 64, t = (int)threadIdx.x - 64;
+    asm volatile("bar.sync 2, %0;" ::"r"(n_epi) : "memory");   // nobody still reads the previous tile's values
+    for (int i = t; i < block_n; i += n_epi) s[i] = (tile * block_n + i < N) ? __ldg(bias + tile * block_n + i) : 0.0f;
+    asm volatile("bar.sync 2, %0;" ::"r"(n_epi) : "memory");
+    nt = tile;
+  }
+  __device__ __forceinline__ const float* at(int col0, int block_n) const { return s + (col0 - nt * block_n); }
+};
+
+// -------------------------------------------------------------------------------------------
 // y = act(acc + bias) written through the TMA unit. A thread owns a ROW of the accumulator, so direct global
 // stores put 32 different cache lines into every store instruction (ncu: 32 sectors/request, LSU-bound
 // epilogue). Here each warp packs its 32x32 chunk into a swizzled shared-memory staging tile (conflict-free
@@ -123,23 +178,28 @@ struct EpiBiasActTma : EpiDefaults {
     const float* bias;                 // [N] or null
     int N;
     int act;                           // 0 none, 1 relu, 2 gelu(erf)
+    const float* pe;                   // [max_len][N] positional table or null: + pe[token_pos[row]] (token embedding)
+    const int* token_pos;              // [M]
+    int M;                             // rows (only read with pe)
   };
   // 16 epilogue warps on 256-column tiles (4 per TMEM lane quarter): the per-chunk chain tcgen05.ld -> math ->
   // staging -> fence -> TMA issue is latency-bound, more warps overlap more of it. One staging buffer per warp.
   static constexpr int kColumnSplit = 4;
   static constexpr int kChunkBytes = BF16_OUT ? 2048 : 4096;
   static constexpr int kBuffers = 1;
-  static constexpr int kExtraSmemBytes = 16 * kBuffers * kChunkBytes;
+  static constexpr int kExtraSmemBytes = 16 * kBuffers * kChunkBytes + 1024;
   uint8_t* stage;
   int buf;
+  BiasTileCache bias_cache;
   __device__ __forceinline__ void setup(const Params&, uint8_t* extra, int warp_slot, int) {
     stage = extra + warp_slot * (kBuffers * kChunkBytes);
     buf = 0;
+    bias_cache.init(extra + 16 * kBuffers * kChunkBytes);
   }
   __device__ __forceinline__ void finish(const Params&, int lane) {
     if (lane == 0) tma_store_wait_read<0>();  // staging must stay valid until the TMA unit has read it
   }
-  __device__ __forceinline__ void begin(const Params&, int, int, int) {}
+  __device__ __forceinline__ void begin(const Params& p, int, int nt, int) { bias_cache.load(p.bias, p.N, nt, block_n_); }
   __device__ __forceinline__ void end(const Params&, int, int, int) {}
   __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int) {
     if (col0 >= p.N) return;  // warp-uniform
@@ -148,10 +208,22 @@ struct EpiBiasActTma : EpiDefaults {
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
     if (p.bias) {
+      const float* sb = bias_cache.at(col0, block_n_);
 #pragma unroll
       for (int i = 0; i < 32; i += 4) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+        const float4 b = *reinterpret_cast<const float4*>(sb + i);
         x[i] += b.x; x[i + 1] += b.y; x[i + 2] += b.z; x[i + 3] += b.w;
+      }
+    }
+    if (p.pe) {
+      const long long grow = (long long)mt * 128 + row;
+      if (grow < p.M) {
+        const float* pr = p.pe + (long long)__ldg(p.token_pos + grow) * p.N + col0;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(pr + i));
+          x[i] += b.x; x[i + 1] += b.y; x[i + 2] += b.z; x[i + 3] += b.w;
+        }
       }
     }
     if (p.act == 1) {
@@ -159,7 +231,11 @@ struct EpiBiasActTma : EpiDefaults {
       for (int i = 0; i < 32; ++i) x[i] = fmaxf(x[i], 0.0f);
     } else if (p.act == 2) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = gelu_erf(x[i]);
+      for (int i = 0; i < 32; i += 2) {
+        const float2 y = gelu_erf2(make_float2(x[i], x[i + 1]));
+        x[i] = y.x;
+        x[i + 1] = y.y;
+      }
     }
     uint8_t* dst = stage + buf * kChunkBytes;
     if (lane == 0) tma_store_wait_read<kBuffers - 1>();  // the store that last used this buffer has read it
@@ -213,9 +289,13 @@ struct EpiConvTransposedTma : EpiDefaults {
   static constexpr int kExtraSmemBytes = 8 * kBuffers * kChunkBytes;
   uint8_t* stage;
   int buf;
+  float bias_row;    // the thread's accumulator row = its output channel never changes: one load for the whole kernel
+  int bias_for;
   __device__ __forceinline__ void setup(const Params&, uint8_t* extra, int warp_slot, int) {
     stage = extra + warp_slot * (kBuffers * kChunkBytes);
     buf = 0;
+    bias_for = -1;
+    bias_row = 0.0f;
   }
   __device__ __forceinline__ void finish(const Params&, int lane) {
     if (lane == 0) tma_store_wait_read<0>();
@@ -226,7 +306,8 @@ struct EpiConvTransposedTma : EpiDefaults {
     const int ch0 = row & ~31;           // first channel of this warp's lane quarter
     if (ch0 >= p.c_out) return;          // warp-uniform: conv2 has only 64 of the 128 accumulator rows
     const int lane = row & 31;
-    const float b = __ldg(p.bias + row);
+    if (bias_for != row) { bias_row = __ldg(p.bias + row); bias_for = row; }
+    const float b = bias_row;
     uint8_t* dst = stage + buf * kChunkBytes;
     if (lane == 0) tma_store_wait_read<kBuffers - 1>();
     __syncwarp();
@@ -258,14 +339,18 @@ struct EpiConvPool16 : EpiDefaults {
     __nv_bfloat16* out_bf16;  // [frames][N]
     int frames, N;
   };
-  __device__ __forceinline__ void begin(const Params&, int, int, int) {}
+  static constexpr int kExtraSmemBytes = 1024;
+  BiasTileCache bias_cache;
+  __device__ __forceinline__ void setup(const Params&, uint8_t* extra, int, int) { bias_cache.init(extra); }
+  __device__ __forceinline__ void begin(const Params& p, int, int nt, int) { bias_cache.load(p.bias, p.N, nt, block_n_); }
   __device__ __forceinline__ void end(const Params&, int, int, int) {}
   __device__ __forceinline__ void chunk(const Params& p, int mt, int col0, int row, uint32_t (&v)[32], int /*pass*/) {
     const int lane = threadIdx.x & 31;
     float x[32];
+    const float* sb = bias_cache.at(col0, block_n_);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+      const float4 b = *reinterpret_cast<const float4*>(sb + i);
       x[i] = fmaxf(__uint_as_float(v[i]) + b.x, 0.0f);
       x[i + 1] = fmaxf(__uint_as_float(v[i + 1]) + b.y, 0.0f);
       x[i + 2] = fmaxf(__uint_as_float(v[i + 2]) + b.z, 0.0f);

@@ -75,33 +75,53 @@ inline std::atomic<int>& pdl_enabled() {
 }
 
 template <class... KArgs, class... Args>
-inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_kernel_cluster(int cluster, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                         Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled().load(std::memory_order_relaxed)) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (cluster > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled().load(std::memory_order_relaxed) ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
+template <class... KArgs, class... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  return launch_kernel_cluster(1, kernel, grid, block, smem, stream, std::forward<Args>(args)...);
+}
 
-template <int BLOCK_N, int BLOCK_K, int STAGES, class Epi, int MT = 1, bool SWAP = false>
+// MCAST = 2: clusters of two CTAs share the B tile (tb must then be a tensor map with a box of BLOCK_N / 2 rows); not
+// available for the row-resident schedule.
+template <int BLOCK_N, int BLOCK_K, int STAGES, class Epi, int MT = 1, bool SWAP = false, int MCAST = 1>
 inline cudaError_t launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& shape,
                                const typename Epi::Params& ep, cudaStream_t stream) {
   using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES, MT>;
   constexpr int kSmem = L::kTotal + Epi::kExtraSmemBytes;
   static_assert(kSmem <= 232448, "shared memory budget");
-  auto kernel = gemm_tcgen05_kernel<BLOCK_N, BLOCK_K, STAGES, Epi, MT, SWAP>;
+  auto kernel = gemm_tcgen05_kernel<BLOCK_N, BLOCK_K, STAGES, Epi, MT, SWAP, MCAST>;
   if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), kSmem); e != cudaSuccess) return e;
-  const int m_super = (shape.m_tiles + MT - 1) / MT;
+  if (MCAST > 1 && (shape.row_resident || shape.b_prefetch_tiles)) return cudaErrorInvalidValue;
+  const int m_super = ((shape.m_tiles + MT - 1) / MT + MCAST - 1) / MCAST;   // (pairs of) super-tiles
   const int total = shape.row_resident ? m_super * shape.n_segments : m_super * shape.n_tiles;
   if (total <= 0) return cudaSuccess;
-  const int grid = total < persistent_grid() ? total : persistent_grid();
-  return launch_kernel(kernel, dim3(grid), dim3(gemm_threads<BLOCK_N, Epi>()), kSmem, stream, ta, tb, shape, ep);
+  const int clusters = persistent_grid() / MCAST;
+  const int grid = (total < clusters ? total : clusters) * MCAST;
+  return launch_kernel_cluster(MCAST, kernel, dim3(grid), dim3(gemm_threads<BLOCK_N, Epi>()), kSmem, stream, ta, tb, shape, ep);
 }
 
 template <int BLOCK_N, int BLOCK_K, int STAGES, int KB, class Epi>
@@ -131,6 +151,21 @@ inline cudaError_t launch_gemm_ares(const CUtensorMap& ta, const CUtensorMap& tb
   if (total <= 0) return cudaSuccess;
   const int grid = total < persistent_grid() ? (int)total : persistent_grid();
   return launch_kernel(kernel, dim3(grid), dim3(gemm_threads<kAresBlockN, Epi>()), kSmem, stream, ta, tb, shape, ep);
+}
+
+template <int STAGES, class Epi>
+inline cudaError_t launch_gemm_ares2(const CUtensorMap& ta, const CUtensorMap& tb, const AresShape& shape,
+                                     const typename Epi::Params& ep, cudaStream_t stream) {
+  using L = Ares2SmemLayout<STAGES>;
+  constexpr int kSmem = L::kTotal + Epi::kExtraSmemBytes;
+  static_assert(kSmem <= 232448, "shared memory budget");
+  auto kernel = gemm_ares2_tcgen05_kernel<STAGES, Epi>;
+  if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), kSmem); e != cudaSuccess) return e;
+  const long long total = (long long)shape.m_super * shape.n_panels;
+  if (total <= 0) return cudaSuccess;
+  const int pairs = persistent_grid() / 2;
+  const int grid = 2 * (total < pairs ? (int)total : pairs);
+  return launch_kernel_cluster(2, kernel, dim3(grid), dim3(gemm_threads<kAres2BlockN, Epi>()), kSmem, stream, ta, tb, shape, ep);
 }
 
 inline GemmShape plain_shape(long long M, int N, int K, int block_n, int block_k, int group_m = 16) {

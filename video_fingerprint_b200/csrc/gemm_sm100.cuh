@@ -123,10 +123,16 @@ struct GemmSmemLayout {
 // streamed from shared memory), so a conv with C_out = 64 / 128 as the N dimension uses only 25 % / 50 % of the
 // tensor pipe; with the channels on M and 256 pixels on N it is 50 % / 100 %. The accumulator then holds
 // [channel][pixel] and the epilogue transposes while staging for the TMA store.
-template <int BLOCK_N, int BLOCK_K, int STAGES, class Epilogue, int MT = 1, bool SWAP = false>
+//
+// MCAST = 2: the kernel runs as clusters of two CTAs that work on neighbouring row (super-)tiles of the SAME column tile
+// in lock step. The B tile (filters / weights) of every K block is then fetched from L2 once per PAIR: each CTA loads
+// half of its rows with a multicast TMA that writes both CTAs' shared memory (tmap_b must have a box of BLOCK_N / 2 rows).
+// A stage is released by a multicast tcgen05.commit that arrives at both CTAs' empty barriers (count 2).
+template <int BLOCK_N, int BLOCK_K, int STAGES, class Epilogue, int MT = 1, bool SWAP = false, int MCAST = 1>
 __global__ void __launch_bounds__(gemm_threads<BLOCK_N, Epilogue>(), 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                     const GemmShape shape_in, const __grid_constant__ typename Epilogue::Params ep) {
+  static_assert(MCAST == 1 || MCAST == 2, "cluster size");
   using L = GemmSmemLayout<BLOCK_N, BLOCK_K, STAGES, MT>;
   static_assert(BLOCK_N % 32 == 0 && BLOCK_N >= 32 && BLOCK_N <= 256, "BLOCK_N");
   static_assert(BLOCK_K == 64 || BLOCK_K == 32 || BLOCK_K == 16, "BLOCK_K");
@@ -154,14 +160,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   // the tile walk runs over super-tiles of MT row tiles
   GemmShape shape = shape_in;
   const int m_tiles_real = shape_in.m_tiles;
-  shape.m_tiles = (shape_in.m_tiles + MT - 1) / MT;
+  shape.m_tiles = ((shape_in.m_tiles + MT - 1) / MT + MCAST - 1) / MCAST;   // the walk runs over (pairs of) super-tiles
+  const int crank = MCAST > 1 ? (int)cluster_ctarank() : 0;
+  const int walk_cta = blockIdx.x / MCAST, walk_n = gridDim.x / MCAST;
+  constexpr uint16_t kMcastMask = (uint16_t)((1u << MCAST) - 1u);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], MCAST);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc_full[i], 1);
@@ -175,6 +184,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (MCAST > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the previous kernel's tail; its results are needed from here on
@@ -184,10 +194,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      TileWalk walk(shape, blockIdx.x, gridDim.x);
+      TileWalk walk(shape, walk_cta, walk_n);
       int mts, nt;
       bool first, last;
       while (walk.next(mts, nt, first, last)) {
+        mts = mts * MCAST + crank;
         int frame0[MT], oh0[MT];
 #pragma unroll
         for (int sub = 0; sub < MT; ++sub) {
@@ -226,7 +237,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               tma_load_2d(&tmap_a, &full_bar[stage], dst, kb * BLOCK_K, (mts * MT + sub) * kBlockM);
             }
           }
-          tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * L::kBBytes, kb * BLOCK_K, nt * BLOCK_N);
+          if constexpr (MCAST > 1) {   // my half of the B rows, written into both CTAs of the pair
+            tma_load_2d_mcast(&tmap_b, &full_bar[stage], smem_b + stage * L::kBBytes + crank * (L::kBBytes / MCAST), kb * BLOCK_K,
+                              nt * BLOCK_N + crank * (BLOCK_N / MCAST), kMcastMask);
+          } else {
+            tma_load_2d(&tmap_b, &full_bar[stage], smem_b + stage * L::kBBytes, kb * BLOCK_K, nt * BLOCK_N);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -238,7 +254,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       int stage = 0;
       uint32_t phase = 0;
       int local = 0;
-      TileWalk walk(shape, blockIdx.x, gridDim.x);
+      TileWalk walk(shape, walk_cta, walk_n);
       int mts, nt;
       bool first, last;
       for (; walk.next(mts, nt, first, last); ++local) {
@@ -266,7 +282,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
             }
           }
-          umma_commit(&empty_bar[stage]);
+          if constexpr (MCAST > 1) umma_commit_mcast(&empty_bar[stage], kMcastMask); else umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&acc_full[acc]);
@@ -280,13 +296,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int row = quarter * 32 + lane;
     const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
     int local = 0;
-    TileWalk walk(shape, blockIdx.x, gridDim.x);
+    TileWalk walk(shape, walk_cta, walk_n);
     int mts, nt;
     bool first, last;
     Epilogue epi;
     uint8_t* extra_smem = smem + L::kCoreAligned;
     epi.setup(ep, extra_smem, warp - 2, lane);
+    epi.set_block_n(BLOCK_N);
     for (; walk.next(mts, nt, first, last); ++local) {
+      mts = mts * MCAST + crank;
       const int acc = local & 1;
       const uint32_t acc_phase = (local >> 1) & 1;
       if (first) epi.item_begin(ep, mts, walk.seg, row, extra_smem);
@@ -321,6 +339,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if constexpr (MCAST > 1) cluster_sync_all();   // my last multicast commits target the peer's barriers: it must still be there
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -478,6 +497,7 @@ gemm_bres_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     int local = 0;
     Epilogue epi;
     epi.setup(ep, smem + L::kCoreAligned, warp - 2, lane);
+    epi.set_block_n(BLOCK_N);
     for (long long u = u0; u < u1; ++u, ++local) {
       const int nt = (int)(u / shape.m_tiles);
       const int mt = (int)(u - (long long)nt * shape.m_tiles);
@@ -540,6 +560,7 @@ struct AresShape {
   int n_panels;
   int tri;            // 1: skip column tiles strictly below the diagonal
   long long q_row0;   // global index of query row 0 (position of the diagonal)
+  int block_n;        // database rows per column tile (128: single-CTA kernel, 256: CTA-pair kernel)
 };
 
 struct AresWalk {
@@ -555,7 +576,7 @@ struct AresWalk {
       cur += stride;
       nt0 = p * s.panel_tiles;
       nt1 = min(s.n_tiles, nt0 + s.panel_tiles);
-      if (s.tri) nt0 = max(nt0, (int)((s.q_row0 + (long long)mts * (kAresMT * kBlockM)) / kAresBlockN));
+      if (s.tri) nt0 = max(nt0, (int)((s.q_row0 + (long long)mts * (kAresMT * kBlockM)) / s.block_n));
       if (nt0 < nt1) return true;
     }
     return false;
@@ -730,6 +751,189 @@ gemm_ares_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =================================================================================================
+// CTA-pair version of the A-resident join kernel (tcgen05 cta_group::2). An SS-mode UMMA streams both operands from shared
+// memory: (128 + N) rows x 32 B per instruction, i.e. 128 B/clk at M128 N128 - the whole shared-memory port, with the TMA
+// fill (32 B/clk here) on top; that is what held the single-CTA kernel at 0.74 of the tensor peak. A pair of CTAs issues
+// ONE UMMA of M = 256, N = 256: each SM computes its 128 query rows against all 256 database rows but keeps only 128 of
+// them (16 KB per K block) in its own shared memory and reads the peer's half over the pair link: 64 B/clk of operand
+// reads + 32 B/clk of fill per SM.
+//   work item = (256 query rows: 128 per CTA, resident) x (one panel of 256-row database tiles), panel-major as above
+//   leader CTA (cluster rank 0): its warp 1 issues every UMMA and commits to BOTH CTAs' barriers (multicast commit);
+//   both producers load their own query rows and their half of each database tile, the byte counts land on the LEADER's
+//   full barriers; both CTAs' epilogue warps drain their own TMEM and arrive on the LEADER's acc_empty barrier.
+// =================================================================================================
+constexpr int kAres2BlockN = 256;
+
+template <int STAGES>
+struct Ares2SmemLayout {
+  static constexpr int kABytes = kBlockM * 128;                   // one K block of this CTA's 128 query rows
+  static constexpr int kAResident = kAresKB * kABytes;            // 64 KB
+  static constexpr int kBBytes = (kAres2BlockN / 2) * 128;        // this CTA's half of one K block of a database tile
+  static constexpr int kCore = kAResident + STAGES * kBBytes + 256;
+  static constexpr int kCoreAligned = (kCore + 1023) / 1024 * 1024;
+  static constexpr int kTotal = kCoreAligned + 1024;
+};
+
+template <int STAGES, class Epilogue>
+__global__ void __launch_bounds__(gemm_threads<kAres2BlockN, Epilogue>(), 1)
+gemm_ares2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                          const AresShape shape, const __grid_constant__ typename Epilogue::Params ep) {
+  using L = Ares2SmemLayout<STAGES>;
+  constexpr int kEpiWarps = 4 * gemm_column_split<kAres2BlockN, Epilogue>();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + L::kAResident;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kAResident + STAGES * L::kBBytes);
+  uint64_t* full_bar = bars;                       // leader's are used (bytes of both CTAs)
+  uint64_t* empty_bar = bars + STAGES;             // per CTA, fed by the leader's multicast commits
+  uint64_t* acc_full = bars + 2 * STAGES;          // per CTA (multicast commit)
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;     // leader's: 2 x kEpiWarps arrivals
+  uint64_t* a_full = bars + 2 * STAGES + 4;        // leader's
+  uint64_t* a_empty = bars + 2 * STAGES + 5;       // per CTA (multicast commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 6);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 2 * kEpiWarps);
+    }
+    mbar_init(a_full, 1);
+    mbar_init(a_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers and TMEM exist before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, a_phase = 0;
+      AresWalk walk(shape, pair, n_pairs);
+      int mts, nt0, nt1;
+      const uint32_t a_full_leader = mapa_u32(a_full, 0);
+      while (walk.next(mts, nt0, nt1)) {
+        mbar_wait(a_empty, a_phase ^ 1);
+        a_phase ^= 1;
+        if (leader) mbar_arrive_expect_tx(a_full, 2 * L::kAResident);
+#pragma unroll
+        for (int kb = 0; kb < kAresKB; ++kb)
+          tma_load_2d_2cta(&tmap_a, a_full_leader, smem_a + kb * L::kABytes, kb * 64, (mts * 2 + (int)crank) * kBlockM);
+        for (int nt = nt0; nt < nt1; ++nt) {
+#pragma unroll
+          for (int kb = 0; kb < kAresKB; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kBBytes);
+            tma_load_2d_2cta(&tmap_b, mapa_u32(&full_bar[stage], 0), smem_b + stage * L::kBBytes, kb * 64,
+                             nt * kAres2BlockN + (int)crank * (kAres2BlockN / 2));
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ UMMA issuer (leader CTA only) ------------------------------
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, kAres2BlockN);
+      int stage = 0, local = 0;
+      uint32_t phase = 0, a_phase = 0;
+      AresWalk walk(shape, pair, n_pairs);
+      int mts, nt0, nt1;
+      const uint32_t a_base = smem_u32(smem_a);
+      while (walk.next(mts, nt0, nt1)) {
+        mbar_wait(a_full, a_phase);
+        a_phase ^= 1;
+        tc_fence_after();
+        for (int nt = nt0; nt < nt1; ++nt, ++local) {
+          const int acc = local & 1;
+          mbar_wait(&acc_empty[acc], ((local >> 1) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * kAres2BlockN;
+#pragma unroll
+          for (int kb = 0; kb < kAresKB; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint64_t adesc = umma_smem_desc_kmajor<128>(a_base + kb * L::kABytes);
+            const uint64_t bdesc = umma_smem_desc_kmajor<128>(smem_u32(smem_b + stage * L::kBBytes));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2cta(&empty_bar[stage], 3);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          umma_commit_2cta(&acc_full[acc], 3);
+        }
+        umma_commit_2cta(a_empty, 3);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs, own TMEM half) ------------------------------
+    constexpr int kSplit = gemm_column_split<kAres2BlockN, Epilogue>();
+    constexpr int kColsPerWarp = kAres2BlockN / kSplit;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
+    int local = 0;
+    AresWalk walk(shape, pair, n_pairs);
+    int mts, nt0, nt1;
+    Epilogue epi;
+    epi.setup(ep, smem + L::kCoreAligned, warp - 2, lane);
+    const uint32_t acc_empty_leader[2] = {mapa_u32(&acc_empty[0], 0), mapa_u32(&acc_empty[1], 0)};
+    while (walk.next(mts, nt0, nt1)) {
+      const int mt = mts * 2 + (int)crank;   // this CTA's 128-row tile
+      for (int nt = nt0; nt < nt1; ++nt, ++local) {
+        const int acc = local & 1;
+        mbar_wait(&acc_full[acc], (local >> 1) & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAres2BlockN;
+        epi.begin(ep, mt, nt, row);
+#pragma unroll 1
+        for (int c = col_begin; c < col_begin + kColsPerWarp; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(taddr + c, v);
+          tmem_ld_wait();
+          epi.chunk(ep, mt, nt * kAres2BlockN + c, row, v, 0);
+        }
+        epi.end(ep, mt, nt, row);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(acc_empty_leader[acc]);
+      }
+    }
+    epi.finish(ep, lane);
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
   }
 }
 

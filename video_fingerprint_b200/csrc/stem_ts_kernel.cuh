@@ -62,7 +62,8 @@ struct StemTsSmem {
   static constexpr int kRaw = kStage + kStemEpiWarps * 2048;             // raw frame planes
   static constexpr int kTile = kRaw + kTsRawSlots * kStemRawSlotBytes;   // 2 HWC tiles
   static constexpr int kBars = kTile + 2 * kStemTileBytes;
-  static constexpr int kTotal = kBars + 512 + 1024;
+  static constexpr int kBias = kBars + 512;              // conv2 bias (64 floats): no L1 is left beside 225 KB of shared memory,
+  static constexpr int kTotal = kBias + 256 + 1024;      // so a __ldg in the epilogue loop is an L2 round trip every time
 };
 static_assert(StemTsSmem::kTotal <= 232448, "stem TS kernel shared memory");
 static_assert(StemTsSmem::kW2 % 1024 == 0 && StemTsSmem::kW1 % 1024 == 0 && StemTsSmem::kStage % 1024 == 0 && StemTsSmem::kRaw % 1024 == 0,
@@ -123,26 +124,6 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* v)
       "r"(v[31])
       : "memory");
 }
-// packed fp32 pairs (FADD2 / FFMA2 on sm_100)
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-  unsigned long long ra, rb, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-  return d;
-}
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long ra, rb, rc, rd;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
-  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  float2 d;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-  return d;
-}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_constant__ StemTsParams p) {
@@ -169,6 +150,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
   uint64_t* raw_full = bars + 32;     // [5] bulk copy -> transposers
   uint64_t* raw_empty = bars + 37;    // [5] transposers -> bulk copy issuer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 42);
+  float* c2_bias_s = reinterpret_cast<float*>(smem + StemTsSmem::kBias);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -179,6 +161,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
 
   for (int i = tid; i < (2 * kStemUnitBytes) / 16; i += kStemThreads) reinterpret_cast<uint4*>(c1buf)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < (2 * kStemTileBytes) / 16; i += kStemThreads) reinterpret_cast<uint4*>(tilebuf)[i] = make_uint4(0, 0, 0, 0);
+  if (tid < 64) c2_bias_s[tid] = __ldg(p.c2_bias + tid);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmap_w2);
     tma_prefetch_desc(&p.tmap_w1);
@@ -392,7 +375,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
         uint32_t q[4];
 #pragma unroll
         for (int i = 0; i < 8; i += 4) {
-          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.c2_bias + col_half * 32 + 8 * c + i));
+          const float4 bb = *reinterpret_cast<const float4*>(c2_bias_s + col_half * 32 + 8 * c + i);
           const float s0 = __shfl_up_sync(0xffffffffu, __uint_as_float(v2[i]), 1), s1 = __shfl_up_sync(0xffffffffu, __uint_as_float(v2[i + 1]), 1);
           const float s2 = __shfl_up_sync(0xffffffffu, __uint_as_float(v2[i + 2]), 1), s3 = __shfl_up_sync(0xffffffffu, __uint_as_float(v2[i + 3]), 1);
           const float2 y01 = ffma2(make_float2(s0, s1), keep2, fadd2(make_float2(__uint_as_float(v0[i]), __uint_as_float(v0[i + 1])), make_float2(bb.x, bb.y)));

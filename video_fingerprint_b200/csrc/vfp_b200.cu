@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "conv1_kernel.cuh"
+#include "ffn_kernel.cuh"
 #include "gemm_launch.cuh"
 #include "join_kernels.cuh"
 #include "metrics_kernels.cuh"
@@ -104,6 +105,7 @@ struct AttnBlockWeights {
   __nv_bfloat16 *wqkv, *wo, *w1, *w2;
   float *bqkv, *bo, *b1, *b2;
   CUtensorMap tm_qkv, tm_o, tm_w1, tm_w2;
+  CUtensorMap tm_w1_ffn, tm_w2_ffn;   // fused feed-forward kernel: boxes of 128 rows x 64 columns (one CTA's half of a 256-row block)
 };
 
 }  // namespace
@@ -119,6 +121,7 @@ struct vfp_weights {
   __nv_bfloat16 *c2_w = nullptr, *c3_w = nullptr, *c4_w = nullptr;
   float *c2_b = nullptr, *c3_b = nullptr, *c4_b = nullptr;
   CUtensorMap tm_c2, tm_c3, tm_c4;
+  CUtensorMap tm_c3h, tm_c4h;   // the same filters with boxes of half the rows: multicast loads of CTA pairs
   __nv_bfloat16* c2f_w = nullptr;  // conv2 weights in the K order of the fused stem kernel
   CUtensorMap tm_c2f;
   __nv_bfloat16* c1ts_w = nullptr;  // conv1 weights stacked for the TS-mode stem kernel: [64 = (sw, c_out)][128 = (kh, 24 window values)]
@@ -252,7 +255,9 @@ int64_t g_stem_pass_frames = kConvPassFrames;
 // default for u8 / bf16 frames; vfp_set_tuning(1, 0) selects the two-kernel path (always used for fp32 frames).
 int g_fused_stem = 2;
 int g_join_prefetch = 16;  // vfp_set_tuning key 5: column tiles of L2 prefetch distance in the join (0 = off)
-int g_join_kernel = 1;      // key 10: 1 = A-resident panel-major kernel, 0 = the generic tile kernel
+int g_ffn_mode = 1;         // key 14: 0 = two GEMM launches, 1 = fused feed-forward kernel on CTA pairs
+int g_conv_mcast = 0;       // key 13: bit 0 conv3, bit 1 conv4 run as CTA pairs that share the filter tile through multicast TMA
+int g_join_kernel = 2;      // key 10: 0 = the generic tile kernel, 1 = A-resident panel-major kernel, 2 = the same on CTA pairs (cta_group::2)
 int g_join_symmetric = 1;   // key 11: self joins screen the upper triangle only
 int g_join_panel_tiles = 512;  // key 12: database column tiles (of 128 rows) per L2 panel
 
@@ -352,7 +357,9 @@ int vfp_set_tuning(int key, long long value) {
   if (key == 5 && value >= 0 && value <= 4096) { g_join_prefetch = (int)value; return 0; }
   if (key == 6 && value >= 0 && value <= 4096) { g_topk_prefetch = (int)value; return 0; }
   if (key == 3 && value >= 64 && value <= kConvPassFrames) { g_conv_pass_frames = value; return 0; }
-  if (key == 10 && value >= 0 && value <= 1) { g_join_kernel = (int)value; return 0; }
+  if (key == 14 && value >= 0 && value <= 1) { g_ffn_mode = (int)value; return 0; }
+  if (key == 13 && value >= 0 && value <= 3) { g_conv_mcast = (int)value; return 0; }
+  if (key == 10 && value >= 0 && value <= 2) { g_join_kernel = (int)value; return 0; }
   if (key == 11 && value >= 0 && value <= 1) { g_join_symmetric = (int)value; return 0; }
   if (key == 12 && value >= 16 && value <= 65536) { g_join_panel_tiles = (int)value; return 0; }
   if (key == 7 && value >= 0 && value <= 1) { pdl_enabled().store((int)value); return 0; }            // programmatic dependent launch
@@ -393,6 +400,17 @@ unsigned int vfp_device_error_word(void) {
   if (v) cudaMemcpyToSymbol(g_vfp_device_error, &zero, sizeof(zero));
   return v;
 }
+
+#ifdef VFP_FFN_TRACE
+int vfp_debug_ffn_trace(long long* out, int max_pairs) {   // development builds only (not declared in the header): copies + clears
+  (void)max_pairs;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_ffn_trace, sizeof(long long) * 8192 / 2);
+  static long long zeros[4096];
+  cudaMemcpyToSymbol(g_ffn_trace, zeros, sizeof(zeros));
+  return 2048;
+}
+#endif
 
 int vfp_debug_hang_log(unsigned int* out, int max_entries) {
   unsigned int n = 0;
@@ -590,6 +608,9 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
         make_tmap_rows_bf16(&a.tm_w1, a.w1, 4 * kDim, kDim, kDim, 256, 64) ||
         make_tmap_rows_bf16(&a.tm_w2, a.w2, kDim, 4 * kDim, 4 * kDim, 256, 64))
       return bail("tensor map encode failed (attention weights)");
+    if (make_tmap_rows_bf16(&a.tm_w1_ffn, a.w1, 4 * kDim, kDim, kDim, 128, 64) ||
+        make_tmap_rows_bf16(&a.tm_w2_ffn, a.w2, kDim, 4 * kDim, 4 * kDim, 128, 64))
+      return bail("tensor map encode failed (feed-forward weights)");
   }
   // ---- pooling + head ----
   {
@@ -628,6 +649,8 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
       make_tmap_rows_bf16(&w->tm_c1ts, w->c1ts_w, 64, 128, 128, 64, 64) ||
       make_tmap_rows_bf16(&w->tm_c3, w->c3_w, 128, 576, 576, 128, 64) ||
       make_tmap_rows_bf16(&w->tm_c4, w->c4_w, 256, 1152, 1152, 256, 64) ||
+      make_tmap_rows_bf16(&w->tm_c3h, w->c3_w, 128, 576, 576, 64, 64) ||
+      make_tmap_rows_bf16(&w->tm_c4h, w->c4_w, 256, 1152, 1152, 128, 64) ||
       make_tmap_rows_bf16(&w->tm_tok, w->wtok, kDim, 256, 256, 256, 64) ||
       make_tmap_rows_bf16(&w->tm_pool, w->wpool, kDim, kDim, kDim, 256, 64))
     return bail("tensor map encode failed (weights)");
@@ -723,7 +746,8 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     if (make_tmap_out(&ep.tmap_out, c3a, (uint64_t)F * 64, 128, true)) return fail("tensor map encode failed (conv3 out)");
     ep.bias = w->c3_b; ep.c_out = 128; ep.pixels_per_tile = 256;
     // channels on M (128), four frames (256 pixels) on N
-    VFP_CUDA((launch_gemm<128, 64, 4, EpiConvTransposedTma, 2, true>(ta, w->tm_c3, s, ep, st)));
+    if (g_conv_mcast & 1) VFP_CUDA((launch_gemm<128, 64, 4, EpiConvTransposedTma, 2, true, 2>(ta, w->tm_c3h, s, ep, st)));
+    else VFP_CUDA((launch_gemm<128, 64, 4, EpiConvTransposedTma, 2, true>(ta, w->tm_c3, s, ep, st)));
     g_prof.mark(kStConv3, st);
   }
   {  // conv4: 8x8x128 -> 4x4x256 + ReLU + global average pool, tile = 8 frames
@@ -734,7 +758,8 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     conv_taps_strided(&s, 2);
     EpiConvPool16::Params ep{};
     ep.bias = w->c4_b; ep.out_bf16 = feat_out; ep.frames = (int)F; ep.N = 256;
-    VFP_CUDA((launch_gemm<256, 64, 4, EpiConvPool16>(ta, w->tm_c4, s, ep, st)));
+    if (g_conv_mcast & 2) VFP_CUDA((launch_gemm<256, 64, 4, EpiConvPool16, 1, false, 2>(ta, w->tm_c4h, s, ep, st)));
+    else VFP_CUDA((launch_gemm<256, 64, 4, EpiConvPool16>(ta, w->tm_c4, s, ep, st)));
     g_prof.mark(kStConv4, st);
   }
   return 0;
@@ -812,10 +837,14 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     }
     return 0;
   };
-  {
-    EpiBiasAct::Params ep{};
-    ep.bias = w->btok; ep.pe = w->pe; ep.token_pos = tok_pos; ep.out_f32 = xa; ep.ld_out = kDim; ep.M = (int)F; ep.N = kDim;
-    if (token_gemm(feat, F, 256, w->tm_tok, kDim, ep)) return 1;
+  {  // fp32 stream written through the TMA store path (row-per-thread fp32 stores touch 32 lines per instruction)
+    CUtensorMap tma;
+    if (make_tmap_rows_bf16(&tma, feat, (uint64_t)F, 256, 256, 128, 64)) return fail("tensor map encode failed (tokens)");
+    EpiBiasActTma<false>::Params ep{};
+    if (make_tmap_out(&ep.tmap_out, xa, (uint64_t)F, kDim, false)) return fail("tensor map encode failed (token embedding out)");
+    ep.bias = w->btok; ep.N = kDim; ep.act = 0; ep.pe = w->pe; ep.token_pos = tok_pos; ep.M = (int)F;
+    GemmShape s = plain_shape(F, kDim, 256, 256, 64, 32);
+    VFP_CUDA((launch_gemm_bres<256, 64, 2, 4, EpiBiasActTma<false>>(tma, w->tm_tok, s, ep, st)));
     g_prof.mark(kStTokEmbed, st);
   }
   // ---- multi-scale temporal convolutions (residual) ----
@@ -841,10 +870,21 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     g_prof.mark(kStOutProj, st);
     VFP_CUDA(launch_kernel(add_layernorm_bf16_kernel, dim3(ln_grid), dim3(256), 0, st, xa, delta, a.ln2_w, a.ln2_b, xn, (int)F));
     g_prof.mark(kStLayerNorm, st);
-    if (token_gemm_bf16(xn, F, kDim, a.tm_w1, 4 * kDim, a.b1, 2, hbuf)) return 1;
-    g_prof.mark(kStMlp1, st);
-    if (token_gemm_bf16(hbuf, F, 4 * kDim, a.tm_w2, kDim, a.b2, 0, delta)) return 1;
-    g_prof.mark(kStMlp2, st);
+    if (g_ffn_mode == 0) {
+      if (token_gemm_bf16(xn, F, kDim, a.tm_w1, 4 * kDim, a.b1, 2, hbuf)) return 1;
+      g_prof.mark(kStMlp1, st);
+      if (token_gemm_bf16(hbuf, F, 4 * kDim, a.tm_w2, kDim, a.b2, 0, delta)) return 1;
+      g_prof.mark(kStMlp2, st);
+    } else {   // both GEMMs in one kernel on CTA pairs, the hidden activation stays on the SM (ffn_kernel.cuh)
+      FfnParams fp{};
+      if (make_tmap_rows_bf16(&fp.tmap_x, xn, (uint64_t)F, kDim, kDim, 128, 64)) return fail("tensor map encode failed (feed-forward)");
+      fp.tmap_w1 = a.tm_w1_ffn; fp.tmap_w2 = a.tm_w2_ffn;
+      fp.b1 = a.b1; fp.b2 = a.b2; fp.out = delta; fp.M = (int)F; fp.pair_tiles = (int)((F + 255) / 256);
+      const int grid = 2 * std::min(fp.pair_tiles, persistent_grid() / 2);
+      VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(ffn_pair_kernel<5>), FfnSmem<5>::kTotal));
+      VFP_CUDA(launch_kernel_cluster(2, ffn_pair_kernel<5>, dim3(grid), dim3(kFfnThreads), FfnSmem<5>::kTotal, st, fp));
+      g_prof.mark(kStMlp1, st);   // reported under the up-projection's stage name; mlp2_gemm stays 0
+    }
   }
   // close the last block's residual and make the bf16 copy the pooling GEMM reads
   VFP_CUDA(launch_kernel(add_convert_bf16_kernel, dim3((unsigned)((F * kDim / 8 + 255) / 256)), dim3(256), 0, st, xa, w->n_attn > 0 ? delta : nullptr, xbf,
@@ -860,7 +900,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     if (make_tmap_out(&ep.tmap_out, logits, (uint64_t)F, kDim, false)) return fail("tensor map encode failed (pool logits)");
     ep.bias = w->bpool; ep.N = kDim; ep.act = 1;
     GemmShape s = plain_shape(F, kDim, kDim, 256, 64, 32);
-    VFP_CUDA((launch_gemm<256, 64, 3, EpiBiasActTma<false>>(tma, w->tm_pool, s, ep, st)));
+    VFP_CUDA((launch_gemm_bres<256, 64, 2, 4, EpiBiasActTma<false>>(tma, w->tm_pool, s, ep, st)));   // the 256 x 256 weight block stays in shared memory
     g_prof.mark(kStPoolGemm, st);
   }
   VFP_CUDA(launch_kernel(temporal_pool_kernel, dim3((unsigned)C), dim3(256), 0, st, xa, logits, d_cu, pooled, pooled_bf));
@@ -1010,23 +1050,27 @@ int vfp_join_threshold(const float* q, const float* db, int64_t n_q, int64_t n_d
   ep.q_rows = n_q; ep.db_rows = n_db; ep.q_row0 = q_row0;
   ep.out_i = cand_i; ep.out_j = cand_j; ep.out_s = cand_s; ep.count = cand_count; ep.capacity = cand_cap;
   CUtensorMap ta, tb;
-  if (g_join_kernel == 1) {   // A-resident, panel-major schedule (gemm_sm100.cuh)
+  if (g_join_kernel >= 1) {   // A-resident, panel-major schedule (gemm_sm100.cuh); 2 = CTA pairs (cta_group::2 UMMAs)
     if (make_tmap_rows_bf16(&ta, qbf, (uint64_t)n_q, 256, 256, 128, 64) ||
         make_tmap_rows_bf16(&tb, dbbf, (uint64_t)n_db, 256, 256, 128, 64))
       return fail("vfp_join_threshold: tensor map encode failed");
+    const bool pairs = g_join_kernel == 2;
     AresShape s{};
-    s.m_super = (int)((n_q + kAresMT * kBlockM - 1) / (kAresMT * kBlockM));
-    s.n_tiles = (int)((n_db + kAresBlockN - 1) / kAresBlockN);
+    s.block_n = pairs ? kAres2BlockN : kAresBlockN;
+    s.m_super = (int)((n_q + kAresMT * kBlockM - 1) / (kAresMT * kBlockM));   // 256 query rows per work item in both kernels
+    s.n_tiles = (int)((n_db + s.block_n - 1) / s.block_n);
     // a panel of <= 65 536 database rows (32 MB of bf16) stays in L2 while every query super-tile passes over it; small
     // problems get shorter panels so that there are enough items to balance the SMs
-    int panel = g_join_panel_tiles;
-    while (panel > 16 && (long long)s.m_super * ((s.n_tiles + panel - 1) / panel) < 16LL * persistent_grid()) panel /= 2;
+    int panel = g_join_panel_tiles * kAresBlockN / s.block_n;
+    const int workers = pairs ? persistent_grid() / 2 : persistent_grid();
+    while (panel > 8 && (long long)s.m_super * ((s.n_tiles + panel - 1) / panel) < 16LL * workers) panel /= 2;
     s.panel_tiles = panel;
     s.n_panels = (s.n_tiles + panel - 1) / panel;
     s.tri = tri;
     s.q_row0 = 0;   // tri compares LOCAL row and column indices: q and db are the same matrix
     ep.tri = tri;
-    VFP_CUDA((launch_gemm_ares<5, EpiJoinThreshold>(ta, tb, s, ep, st)));
+    if (pairs) VFP_CUDA((launch_gemm_ares2<8, EpiJoinThreshold>(ta, tb, s, ep, st)));
+    else VFP_CUDA((launch_gemm_ares<5, EpiJoinThreshold>(ta, tb, s, ep, st)));
   } else {
     if (make_tmap_rows_bf16(&ta, qbf, (uint64_t)n_q, 256, 256, 128, 64) ||
         make_tmap_rows_bf16(&tb, dbbf, (uint64_t)n_db, 256, 256, 256, 64))
