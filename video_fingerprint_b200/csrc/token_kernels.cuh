@@ -219,16 +219,30 @@ temporal_conv_kernel(const float* __restrict__ x, const int* __restrict__ tok_po
 }
 
 // ---------------------------------------------------------------------------------------------
-// Multi-head self-attention over one clip (model.py:143), flash-style on the register-fragment tensor path
-// (mma.sync m16n8k16 bf16 -> fp32): head_dim 32 and T <= ~500 make every (clip, head) problem a few 64x64x32
-// tiles - far too small for a 128-row UMMA tile, and the whole stage is < 1 % of the forward FLOPs.
-// grid = (clip, head, 64-query block); 4 warps x 16 query rows; keys are walked in blocks of 64 with an online
-// softmax, so any clip length works. qkv: [tokens][768] bf16 = [Q | K | V], head h = columns 32h..32h+31.
+// Multi-head self-attention (model.py:143) over PACKED clips, flash-style on the register-fragment tensor path
+// (mma.sync m16n8k16 bf16 -> fp32). head_dim is 32, so QK^T and PV of one head are 128 x 128 x 32 problems: a 128-row UMMA
+// tile would spend its time in TMEM round trips and mbarrier hand-offs (a chain of ~2 600 cycles per head and key block,
+// estimated from the hand-off costs measured in profiles/r01_microbench_handoff.txt), while eight warps with the scores in
+// registers need ~4 000 HMMA cycles per 128 tokens for all eight heads - and the whole stage is 0.7 % of the forward's FLOPs.
+//
+// A CTA owns one ITEM = 64 consecutive query tokens of ONE clip (the host lists the items: ceil(T / 64) per clip) and walks that
+// clip's keys in blocks of 64 tokens from the clip's first token, so what a clip gets never depends on what it is packed next
+// to - bit for bit. Per head and key block the Q / K / V slices (64 rows x 64 B each) are staged in shared memory with cp.async
+// through a 4-stage ring (three steps of loads in flight per CTA, three CTAs per SM: the kernel moves 2 KB per token and was
+// latency-bound with two stages), 80-byte row pitch -> conflict-free ldmatrix, K fragments come from ldmatrix, V fragments
+// from ldmatrix.trans (no transposed copy), P goes from the score accumulators straight into the A fragments of the PV
+// product. Only the clip's last key block needs a mask.
+// (Round 1: one CTA per (clip, head, 64 queries), Q fragments from strided 4-byte global loads, V transposed with scalar
+// shared-memory stores: 2.6 ms per 10 000 clips = 64 TFLOP/s.)
+// qkv: [tokens][768] bf16 = [Q | K | V], head h = columns 32h .. 32h+31. Softmax in the exp2 domain, fp32.
 // ---------------------------------------------------------------------------------------------
-constexpr int kAttQ = 64;
-constexpr int kAttKeys = 64;
-constexpr int kAttKPitch = 40;             // bf16 per K row in smem: 32 + 8 pad -> conflict-free fragment loads
-constexpr int kAttVPitch = kAttKeys + 8;   // bf16 per V^T row
+constexpr int kAttRows = 64;                          // query tokens per CTA = key tokens per block
+constexpr int kAttThreads = 128;                      // 4 warps x 16 query rows
+constexpr int kAttPitch = 40;                         // bf16 per shared-memory row: 32 + 8 pad
+constexpr int kAttTileElems = kAttRows * kAttPitch;   // one of Q / K / V
+constexpr int kAttStageBytes = 3 * kAttTileElems * 2; // 15 360
+constexpr int kAttStages = 4;                         // three (head, key block) steps of loads in flight per CTA
+constexpr int kAttSmemBytes = kAttStages * kAttStageBytes;   // 61 440: three CTAs per SM
 
 __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -236,134 +250,178 @@ __device__ __forceinline__ void mma_16816(float (&d)[4], const uint32_t (&a)[4],
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_row)));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(smem_row)));
+}
+// 16-byte asynchronous copy; src_bytes = 0 zero-fills the destination (rows past the end of the token buffer)
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ float fast_exp2(float x) {   // one MUFU.EX2; exp2(-inf) = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-__global__ void __launch_bounds__(128)
-attention_mma_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ cu, __nv_bfloat16* __restrict__ out) {
-  __shared__ __align__(16) __nv_bfloat16 Ks[kAttKeys * kAttKPitch];
-  __shared__ __align__(16) __nv_bfloat16 Vt[kHeadDim * kAttVPitch];
+__global__ void __launch_bounds__(kAttThreads, 3)
+attention_fa_kernel(const __nv_bfloat16* __restrict__ qkv, const int4* __restrict__ items /*{first query token, clip start, clip end, 0}*/,
+                    __nv_bfloat16* __restrict__ out, int n_tokens) {
+  extern __shared__ __align__(16) uint8_t att_smem[];
   pdl_launch_dependents();
   pdl_wait();
-  const int clip = blockIdx.x, head = blockIdx.y;
-  const int t0 = cu[clip];
-  const int T = cu[clip + 1] - t0;
-  const int q0 = blockIdx.z * kAttQ;
-  if (q0 >= T) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, tig = lane & 3;
+  const int4 item = __ldg(items + blockIdx.x);
+  const int q0 = item.x, k_begin = item.y, k_end = item.z;
+  const int r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8;   // this thread's two query rows (valid below k_end)
+  const bool warp_live = q0 + warp * 16 < k_end;          // a warp whose 16 rows lie past the clip only helps with the loads
+  const int n_kblocks = (k_end - k_begin + kAttRows - 1) / kAttRows;
+  const int n_steps = kHeads * n_kblocks;
   const size_t row_stride = 3 * kDim;
-  const __nv_bfloat16* base = qkv + (size_t)t0 * row_stride + head * kHeadDim;
 
-  // Q fragments (A operand) for rows r_lo = q0 + 16*warp + g and r_lo + 8; rows past the clip read row T-1 (never stored)
-  const int r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8;
-  const __nv_bfloat16* q_lo = base + (size_t)min(r_lo, T - 1) * row_stride;
-  const __nv_bfloat16* q_hi = base + (size_t)min(r_hi, T - 1) * row_stride;
-  uint32_t qa[2][4];
+  auto load_stage = [&](int step) {   // step = head * n_kblocks + key block; an empty commit keeps the group count uniform
+    if (step < n_steps) {
+      const int h = step / n_kblocks, j = step - h * n_kblocks;
+      __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(att_smem + (step % kAttStages) * kAttStageBytes);
+      const int kbase = k_begin + j * kAttRows;
 #pragma unroll
-  for (int ks = 0; ks < 2; ++ks) {
-    qa[ks][0] = *reinterpret_cast<const uint32_t*>(q_lo + 16 * ks + 2 * tig);
-    qa[ks][1] = *reinterpret_cast<const uint32_t*>(q_hi + 16 * ks + 2 * tig);
-    qa[ks][2] = *reinterpret_cast<const uint32_t*>(q_lo + 16 * ks + 2 * tig + 8);
-    qa[ks][3] = *reinterpret_cast<const uint32_t*>(q_hi + 16 * ks + 2 * tig + 8);
-  }
+      for (int it = 0; it < 6; ++it) {
+        const int idx = threadIdx.x + it * kAttThreads;   // 0 .. 767: tile (0 Q, 1 K, 2 V), row, 16-byte piece
+        const int tile = idx >> 8, row = (idx >> 2) & 63, piece = idx & 3;
+        const int token = (tile == 0 ? q0 : kbase) + row;
+        const bool ok = token < n_tokens;
+        const __nv_bfloat16* src = qkv + (size_t)(ok ? token : 0) * row_stride + tile * kDim + h * kHeadDim + piece * 8;
+        cp_async_16(st + tile * kAttTileElems + row * kAttPitch + piece * 8, src, ok ? 16 : 0);
+      }
+    }
+    cp_async_commit();
+  };
+
   const float sl2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
   float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
   float o[4][4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[j][i] = 0.f;
+  const int lm = lane >> 3, lr = lane & 7;   // ldmatrix: this lane supplies row lr of matrix lm
 
-  for (int k0 = 0; k0 < T; k0 += kAttKeys) {
-    __syncthreads();  // previous block fully consumed
-    for (int i = threadIdx.x; i < kAttKeys * 4; i += 128) {
-      const int key = i >> 2, c = i & 3;
-      uint4 kq = make_uint4(0, 0, 0, 0), vq = make_uint4(0, 0, 0, 0);
-      if (k0 + key < T) {
-        const uint4* src = reinterpret_cast<const uint4*>(base + (size_t)(k0 + key) * row_stride);
-        kq = src[kDim / 8 + c];
-        vq = src[2 * kDim / 8 + c];
+#pragma unroll
+  for (int pre = 0; pre < kAttStages - 1; ++pre) load_stage(pre);
+  for (int step = 0; step < n_steps; ++step) {
+    const int h = step / n_kblocks, j = step - h * n_kblocks;
+    cp_async_wait<kAttStages - 2>();   // this step's group has landed (the newer ones may still be in flight)
+    __syncthreads();                   // ... for every thread's part, and everyone is done with the stage refilled below
+    load_stage(step + kAttStages - 1);
+    const __nv_bfloat16* Qs = reinterpret_cast<const __nv_bfloat16*>(att_smem + (step % kAttStages) * kAttStageBytes);
+    const __nv_bfloat16* Ks = Qs + kAttTileElems;
+    const __nv_bfloat16* Vs = Ks + kAttTileElems;
+    if (j == 0) {
+      m_lo = m_hi = -INFINITY;
+      l_lo = l_hi = 0.f;
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) o[a][b] = 0.f;
+    }
+    const int kbase = k_begin + j * kAttRows;   // first key token of this block
+    if (warp_live) {
+      // Q fragments of this warp's 16 rows (A operand, two K steps of 16 dims)
+      uint32_t qa[2][4];
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) ldmatrix_x4(qa[ks], Qs + (warp * 16 + (lm & 1) * 8 + lr) * kAttPitch + 16 * ks + (lm >> 1) * 8);
+      // S = Q K^T for 64 keys: 8 n-tiles of 8 keys
+      float s[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        uint32_t kb[4];   // keys 8nt .. 8nt+7; dims 0-7, 8-15, 16-23, 24-31
+        ldmatrix_x4(kb, Ks + (nt * 8 + lr) * kAttPitch + lm * 8);
+        mma_16816(s[nt], qa[0], kb[0], kb[1]);
+        mma_16816(s[nt], qa[1], kb[2], kb[3]);
       }
-      *reinterpret_cast<uint4*>(Ks + key * kAttKPitch + c * 8) = kq;
-      const __nv_bfloat16* ve = reinterpret_cast<const __nv_bfloat16*>(&vq);
+      // keys past the end of the clip (only in its last block) are masked; block row maxima of the RAW scores - the
+      // 1/sqrt(d) log2(e) factor is folded into the exp2
+      float mx_lo = -INFINITY, mx_hi = -INFINITY;
+      if (kbase + kAttRows <= k_end) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) Vt[(c * 8 + e) * kAttVPitch + key] = ve[e];
-    }
-    __syncthreads();
-
-    // S = Q K^T for 64 keys: 8 n-tiles of 8 keys
-    float s[8][4];
+        for (int nt = 0; nt < 8; ++nt) {
+          mx_lo = fmaxf(mx_lo, fmaxf(s[nt][0], s[nt][1]));
+          mx_hi = fmaxf(mx_hi, fmaxf(s[nt][2], s[nt][3]));
+        }
+      } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-      const __nv_bfloat16* kr = Ks + (8 * j + g) * kAttKPitch + 2 * tig;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-        mma_16816(s[j], qa[ks], *reinterpret_cast<const uint32_t*>(kr + 16 * ks), *reinterpret_cast<const uint32_t*>(kr + 16 * ks + 8));
-    }
-    // scale to log2 domain, mask keys past the clip, block row maxima
-    float mx_lo = -INFINITY, mx_hi = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int key = k0 + 8 * j + 2 * tig;
-      const bool v0 = key < T, v1 = key + 1 < T;
-      s[j][0] = v0 ? s[j][0] * sl2 : -INFINITY;
-      s[j][1] = v1 ? s[j][1] * sl2 : -INFINITY;
-      s[j][2] = v0 ? s[j][2] * sl2 : -INFINITY;
-      s[j][3] = v1 ? s[j][3] * sl2 : -INFINITY;
-      mx_lo = fmaxf(mx_lo, fmaxf(s[j][0], s[j][1]));
-      mx_hi = fmaxf(mx_hi, fmaxf(s[j][2], s[j][3]));
-    }
-    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
-    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
-    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
-    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
-    const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);  // finite: key k0 is always valid
-    const float c_lo = exp2f(m_lo - mn_lo), c_hi = exp2f(m_hi - mn_hi);
-    m_lo = mn_lo;
-    m_hi = mn_hi;
-    l_lo *= c_lo;
-    l_hi *= c_hi;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      o[j][0] *= c_lo; o[j][1] *= c_lo; o[j][2] *= c_hi; o[j][3] *= c_hi;
-    }
-    // P = exp2(S - m); O += P V  (P re-used straight from the accumulator registers as the A operand)
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      uint32_t pa[4];
-      float p[2][4];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int j = 2 * kk + h;
-        p[h][0] = exp2f(s[j][0] - m_lo);
-        p[h][1] = exp2f(s[j][1] - m_lo);
-        p[h][2] = exp2f(s[j][2] - m_hi);
-        p[h][3] = exp2f(s[j][3] - m_hi);
-        l_lo += p[h][0] + p[h][1];
-        l_hi += p[h][2] + p[h][3];
+        for (int nt = 0; nt < 8; ++nt) {
+          const int key = kbase + 8 * nt + 2 * tig;
+          if (key >= k_end) s[nt][0] = s[nt][2] = -INFINITY;
+          if (key + 1 >= k_end) s[nt][1] = s[nt][3] = -INFINITY;
+          mx_lo = fmaxf(mx_lo, fmaxf(s[nt][0], s[nt][1]));
+          mx_hi = fmaxf(mx_hi, fmaxf(s[nt][2], s[nt][3]));
+        }
       }
-      pa[0] = pack_bf16x2(p[0][0], p[0][1]);
-      pa[1] = pack_bf16x2(p[0][2], p[0][3]);
-      pa[2] = pack_bf16x2(p[1][0], p[1][1]);
-      pa[3] = pack_bf16x2(p[1][2], p[1][3]);
+      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+      mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+      mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+      // running maxima live in the scaled (log2) domain; every block holds at least one valid key, so they are finite
+      const float mn_lo = fmaxf(m_lo, mx_lo * sl2), mn_hi = fmaxf(m_hi, mx_hi * sl2);
+      const float ms_lo = mn_lo, ms_hi = mn_hi;
+      const float c_lo = fast_exp2(m_lo - ms_lo), c_hi = fast_exp2(m_hi - ms_hi);
+      m_lo = mn_lo;
+      m_hi = mn_hi;
+      l_lo *= c_lo;
+      l_hi *= c_hi;
 #pragma unroll
       for (int jd = 0; jd < 4; ++jd) {
-        const __nv_bfloat16* vr = Vt + (8 * jd + g) * kAttVPitch + 16 * kk + 2 * tig;
-        mma_16816(o[jd], pa, *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+        o[jd][0] *= c_lo; o[jd][1] *= c_lo; o[jd][2] *= c_hi; o[jd][3] *= c_hi;
+      }
+      // P = exp2(S - m); O += P V  (P goes from the accumulator registers straight into the A fragments)
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t pa[4];
+        float p[2][4];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int nt = 2 * kk + hh;
+          p[hh][0] = fast_exp2(fmaf(s[nt][0], sl2, -ms_lo));
+          p[hh][1] = fast_exp2(fmaf(s[nt][1], sl2, -ms_lo));
+          p[hh][2] = fast_exp2(fmaf(s[nt][2], sl2, -ms_hi));
+          p[hh][3] = fast_exp2(fmaf(s[nt][3], sl2, -ms_hi));
+          l_lo += p[hh][0] + p[hh][1];
+          l_hi += p[hh][2] + p[hh][3];
+        }
+        pa[0] = pack_bf16x2(p[0][0], p[0][1]);
+        pa[1] = pack_bf16x2(p[0][2], p[0][3]);
+        pa[2] = pack_bf16x2(p[1][0], p[1][1]);
+        pa[3] = pack_bf16x2(p[1][2], p[1][3]);
+        // V fragments (B operand, 16 keys x 8 dims per n-tile) through ldmatrix.trans: matrices (keys 0-7 | 8-15) x (dims 8jd | 8jd+8)
+#pragma unroll
+        for (int jp = 0; jp < 2; ++jp) {
+          uint32_t vb[4];
+          ldmatrix_x4_trans(vb, Vs + (kk * 16 + (lm & 1) * 8 + lr) * kAttPitch + (2 * jp + (lm >> 1)) * 8);
+          mma_16816(o[2 * jp], pa, vb[0], vb[1]);
+          mma_16816(o[2 * jp + 1], pa, vb[2], vb[3]);
+        }
       }
     }
-  }
-  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 1);
-  l_lo += __shfl_xor_sync(0xffffffffu, l_lo, 2);
-  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 1);
-  l_hi += __shfl_xor_sync(0xffffffffu, l_hi, 2);
-  const float i_lo = 1.0f / l_lo, i_hi = 1.0f / l_hi;
-  __nv_bfloat16* o_lo = out + (size_t)(t0 + r_lo) * kDim + head * kHeadDim + 2 * tig;
-  __nv_bfloat16* o_hi = out + (size_t)(t0 + r_hi) * kDim + head * kHeadDim + 2 * tig;
+    if (j == n_kblocks - 1 && warp_live) {   // last key block of this head: normalise and store this head's 32 output columns
+      float t_lo = l_lo, t_hi = l_hi;
+      t_lo += __shfl_xor_sync(0xffffffffu, t_lo, 1);
+      t_lo += __shfl_xor_sync(0xffffffffu, t_lo, 2);
+      t_hi += __shfl_xor_sync(0xffffffffu, t_hi, 1);
+      t_hi += __shfl_xor_sync(0xffffffffu, t_hi, 2);
+      const float i_lo = 1.0f / t_lo, i_hi = 1.0f / t_hi;
+      __nv_bfloat16* o_lo = out + (size_t)r_lo * kDim + h * kHeadDim + 2 * tig;
+      __nv_bfloat16* o_hi = out + (size_t)r_hi * kDim + h * kHeadDim + 2 * tig;
 #pragma unroll
-  for (int jd = 0; jd < 4; ++jd) {
-    if (r_lo < T) *reinterpret_cast<uint32_t*>(o_lo + 8 * jd) = pack_bf16x2(o[jd][0] * i_lo, o[jd][1] * i_lo);
-    if (r_hi < T) *reinterpret_cast<uint32_t*>(o_hi + 8 * jd) = pack_bf16x2(o[jd][2] * i_hi, o[jd][3] * i_hi);
+      for (int jd = 0; jd < 4; ++jd) {
+        if (r_lo < k_end) *reinterpret_cast<uint32_t*>(o_lo + 8 * jd) = pack_bf16x2(o[jd][0] * i_lo, o[jd][1] * i_lo);
+        if (r_hi < k_end) *reinterpret_cast<uint32_t*>(o_hi + 8 * jd) = pack_bf16x2(o[jd][2] * i_hi, o[jd][3] * i_hi);
+      }
+    }
   }
 }
 

@@ -262,7 +262,7 @@ int g_join_symmetric = 1;   // key 11: self joins screen the upper triangle only
 int g_join_panel_tiles = 512;  // key 12: database column tiles (of 128 rows) per L2 panel
 
 struct TokenWs {
-  size_t cu, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, h, logits, xbf, pooled, pooled_bf, head_h, total;
+  size_t cu, att_items, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, h, logits, xbf, pooled, pooled_bf, head_h, total;
 };
 struct ConvWs {
   size_t c1, c2, c3, total;
@@ -276,6 +276,7 @@ TokenWs token_ws_layout(int64_t F, int64_t C) {
     return o;
   };
   L.cu = take((size_t)(C + 1) * 4);
+  L.att_items = take((size_t)(F / 64 + C + 1) * 16);   // attention work items: <= F / 64 + C of them
   L.tok_pos = take((size_t)F * 4);
   L.tok_len = take((size_t)F * 4);
   L.feat = take((size_t)F * 256 * 2);
@@ -799,6 +800,16 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   g_prof.mark(-1, st);
   g_prof.launches += 8 + 7 * (unsigned long long)w->n_attn;
   VFP_CUDA(cudaMemcpyAsync(d_cu, cu_rel.data(), (size_t)(C + 1) * 4, cudaMemcpyHostToDevice, st));
+  // attention work items: 64 query tokens of one clip each, {first query token, clip start, clip end, 0}
+  std::vector<int32_t> items_host;
+  items_host.reserve((size_t)(F / kAttRows + C) * 4);
+  for (int i = 0; i < C; ++i)
+    for (int q = cu_rel[i]; q < cu_rel[i + 1]; q += kAttRows) {
+      items_host.push_back(q); items_host.push_back(cu_rel[i]); items_host.push_back(cu_rel[i + 1]); items_host.push_back(0);
+    }
+  const size_t n_items = items_host.size() / 4;
+  int4* att_items = reinterpret_cast<int4*>(ws + L.att_items);
+  VFP_CUDA(cudaMemcpyAsync(att_items, items_host.data(), items_host.size() * 4, cudaMemcpyHostToDevice, st));
   // cu_rel is pageable: the copy is staged before the call returns, so the vector may die with this scope.
   VFP_CUDA(launch_kernel(token_map_kernel, dim3((unsigned)((F + 255) / 256)), dim3(256), 0, st, d_cu, C, (int)F, tok_pos, tok_len));
   g_prof.mark(kStMisc, st);
@@ -856,7 +867,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   }
   // ---- attention blocks ----
   const unsigned ln_grid = (unsigned)((F * 32 + 255) / 256);
-  const dim3 att_grid((unsigned)C, kHeads, (unsigned)((max_T + kAttQ - 1) / kAttQ));
+  VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_fa_kernel), kAttSmemBytes));
   // residual updates travel as bf16 `delta` and are folded into the fp32 stream by the next LayerNorm (see there)
   for (int b = 0; b < w->n_attn; ++b) {
     const AttnBlockWeights& a = w->attn[b];
@@ -864,7 +875,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     g_prof.mark(kStLayerNorm, st);
     if (token_gemm_bf16(xn, F, kDim, a.tm_qkv, 3 * kDim, a.bqkv, 0, qkv)) return 1;
     g_prof.mark(kStQkv, st);
-    VFP_CUDA(launch_kernel(attention_mma_kernel, att_grid, dim3(128), 0, st, qkv, d_cu, att));
+    VFP_CUDA(launch_kernel(attention_fa_kernel, dim3((unsigned)n_items), dim3(kAttThreads), kAttSmemBytes, st, qkv, att_items, att, (int)F));
     g_prof.mark(kStAttention, st);
     if (token_gemm_bf16(att, F, kDim, a.tm_o, kDim, a.bo, 0, delta)) return 1;
     g_prof.mark(kStOutProj, st);
