@@ -168,6 +168,23 @@ inline cudaError_t launch_gemm_ares2(const CUtensorMap& ta, const CUtensorMap& t
   return launch_kernel_cluster(2, kernel, dim3(grid), dim3(gemm_threads<kAres2BlockN, Epi>()), kSmem, stream, ta, tb, shape, ep);
 }
 
+// CTA-pair GEMM (BLOCK_N = 256): `tb` must be a tensor map with a box of 128 rows (one CTA's half of the B tile)
+template <int BLOCK_K, int STAGES, class Epi>
+inline cudaError_t launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& shape,
+                                    const typename Epi::Params& ep, cudaStream_t stream) {
+  using L = GemmPairSmemLayout<BLOCK_K, STAGES>;
+  constexpr int kSmem = L::kTotal + Epi::kExtraSmemBytes;
+  static_assert(kSmem <= 232448, "shared memory budget");
+  auto kernel = gemm_pair_tcgen05_kernel<BLOCK_K, STAGES, Epi>;
+  if (cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), kSmem); e != cudaSuccess) return e;
+  if (shape.row_resident || shape.b_prefetch_tiles) return cudaErrorInvalidValue;
+  const long long total = (long long)((shape.m_tiles + 1) / 2) * shape.n_tiles;
+  if (total <= 0) return cudaSuccess;
+  const int pairs = persistent_grid() / 2;
+  const int grid = 2 * (total < pairs ? (int)total : pairs);
+  return launch_kernel_cluster(2, kernel, dim3(grid), dim3(gemm_threads<256, Epi>()), kSmem, stream, ta, tb, shape, ep);
+}
+
 inline GemmShape plain_shape(long long M, int N, int K, int block_n, int block_k, int group_m = 16) {
   GemmShape s{};
   s.m_tiles = (int)((M + kBlockM - 1) / kBlockM);

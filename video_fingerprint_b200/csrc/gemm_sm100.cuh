@@ -937,4 +937,191 @@ gemm_ares2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gr
   }
 }
 
+// =================================================================================================
+// CTA-pair version of the generic kernel (tcgen05 cta_group::2): one UMMA of M = 256, N = 256 per K step for a PAIR of
+// neighbouring 128-row tiles. Each CTA loads its own A tile and HALF of the B tile (128 of the 256 rows) per K block, so a
+// stage is 32 KB instead of 48 KB, the shared-memory port carries 64 B/clk of operand reads instead of 96 B/clk, and six
+// stages fit where four did. Same roles and schedule as gemm_tcgen05_kernel (plain tile order, A as rows or as a 4-D
+// convolution box); the leader CTA (cluster rank 0) issues, commits are multicast, both producers report their bytes to
+// the leader's full barriers, both CTAs' epilogue warps drain their own TMEM and arrive on the leader's acc_empty.
+// =================================================================================================
+template <int BLOCK_K, int STAGES>
+struct GemmPairSmemLayout {
+  static constexpr int kRowBytes = BLOCK_K * 2;
+  static constexpr int kABytes = kBlockM * kRowBytes;
+  static constexpr int kBBytes = 128 * kRowBytes;          // this CTA's half of the 256-row B tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kCore = STAGES * kStageBytes + 256;
+  static constexpr int kCoreAligned = (kCore + 1023) / 1024 * 1024;
+  static constexpr int kTotal = kCoreAligned + 1024;
+};
+
+template <int BLOCK_K, int STAGES, class Epilogue>
+__global__ void __launch_bounds__(gemm_threads<256, Epilogue>(), 1)
+gemm_pair_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                         const GemmShape shape_in, const __grid_constant__ typename Epilogue::Params ep) {
+  constexpr int BLOCK_N = 256;
+  using L = GemmPairSmemLayout<BLOCK_K, STAGES>;
+  constexpr int kEpiWarps = 4 * gemm_column_split<BLOCK_N, Epilogue>();
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * L::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
+  uint64_t* full_bar = bars;                     // leader's are used (bytes of both CTAs)
+  uint64_t* empty_bar = bars + STAGES;           // per CTA (multicast commit)
+  uint64_t* acc_full = bars + 2 * STAGES;        // per CTA (multicast commit)
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;   // leader's: 2 x kEpiWarps arrivals
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+  pdl_launch_dependents();
+  GemmShape shape = shape_in;
+  const int m_tiles_real = shape_in.m_tiles;
+  shape.m_tiles = (shape_in.m_tiles + 1) / 2;   // the walk runs over pairs of row tiles
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 2 * kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2cta(tmem_slot, 512);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer (both CTAs) ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      TileWalk walk(shape, pair, n_pairs);
+      int mp, nt;
+      bool first, last;
+      while (walk.next(mp, nt, first, last)) {
+        const int mt = mp * 2 + (int)crank;
+        int frame0 = 0, oh0 = 0;
+        if (shape.a_conv) {
+          if (shape.tiles_per_frame > 1) {
+            frame0 = mt / shape.tiles_per_frame;
+            oh0 = (mt - frame0 * shape.tiles_per_frame) * shape.tile_out_rows;
+          } else {
+            frame0 = mt * shape.frames_per_tile;
+          }
+        }
+        for (int kb = 0; kb < shape.k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          const uint32_t full_leader = mapa_u32(&full_bar[stage], 0);
+          uint8_t* dst = smem_a + stage * L::kABytes;
+          if (shape.a_conv) {
+            tma_load_4d_2cta(&tmap_a, full_leader, dst, shape.tap_c_blk[kb] * BLOCK_K, shape.tap_w[kb],
+                             shape.h_mul * oh0 + shape.tap_h[kb], frame0);
+          } else {
+            tma_load_2d_2cta(&tmap_a, full_leader, dst, kb * BLOCK_K, mt * kBlockM);
+          }
+          tma_load_2d_2cta(&tmap_b, full_leader, smem_b + stage * L::kBBytes, kb * BLOCK_K, nt * BLOCK_N + (int)crank * 128);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ UMMA issuer (leader CTA only) ------------------------------
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * kBlockM, BLOCK_N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int local = 0;
+      TileWalk walk(shape, pair, n_pairs);
+      int mp, nt;
+      bool first, last;
+      for (; walk.next(mp, nt, first, last); ++local) {
+        const int acc = local & 1;
+        mbar_wait(&acc_empty[acc], ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < shape.k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc_kmajor<L::kRowBytes>(smem_u32(smem_a + stage * L::kABytes));
+          const uint64_t bdesc = umma_smem_desc_kmajor<L::kRowBytes>(smem_u32(smem_b + stage * L::kBBytes));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) umma_bf16_2cta(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2cta(&empty_bar[stage], 3);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2cta(&acc_full[acc], 3);
+      }
+    }
+  } else {
+    // ------------------------------ epilogue (both CTAs, own 128 rows) ------------------------------
+    constexpr int kSplit = gemm_column_split<BLOCK_N, Epilogue>();
+    constexpr int kColsPerWarp = BLOCK_N / kSplit;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const int col_begin = ((warp - 2) >> 2) * kColsPerWarp;
+    int local = 0;
+    TileWalk walk(shape, pair, n_pairs);
+    int mp, nt;
+    bool first, last;
+    Epilogue epi;
+    uint8_t* extra_smem = smem + L::kCoreAligned;
+    epi.setup(ep, extra_smem, warp - 2, lane);
+    epi.set_block_n(BLOCK_N);
+    const uint32_t acc_empty_leader[2] = {mapa_u32(&acc_empty[0], 0), mapa_u32(&acc_empty[1], 0)};
+    for (; walk.next(mp, nt, first, last); ++local) {
+      const int mt = mp * 2 + (int)crank;
+      const int acc = local & 1;
+      mbar_wait(&acc_full[acc], (local >> 1) & 1);
+      tc_fence_after();
+      if (mt < m_tiles_real) {   // the odd tile out of the last pair has no rows: nothing to write (warp-uniform, whole CTA)
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * BLOCK_N;
+        epi.begin(ep, mt, nt, row);
+#pragma unroll 1
+        for (int pass = 0; pass < Epilogue::kPasses; ++pass) {
+#pragma unroll 1
+          for (int c = col_begin; c < col_begin + kColsPerWarp; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(taddr + c, v);
+            tmem_ld_wait();
+            epi.chunk(ep, mt, nt * BLOCK_N + c, row, v, pass);
+          }
+        }
+        epi.end(ep, mt, nt, row);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc_empty_leader[acc]);
+    }
+    epi.finish(ep, lane);
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, 512);
+  }
+}
+
 }  // namespace vfp

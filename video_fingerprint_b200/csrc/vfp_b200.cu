@@ -105,6 +105,7 @@ struct AttnBlockWeights {
   __nv_bfloat16 *wqkv, *wo, *w1, *w2;
   float *bqkv, *bo, *b1, *b2;
   CUtensorMap tm_qkv, tm_o, tm_w1, tm_w2;
+  CUtensorMap tm_qkv_h, tm_o_h;       // the same weights with boxes of 128 rows: CTA-pair GEMM (one CTA's half of a 256-row tile)
   CUtensorMap tm_w1_ffn, tm_w2_ffn;   // fused feed-forward kernel: boxes of 128 rows x 64 columns (one CTA's half of a 256-row block)
 };
 
@@ -255,6 +256,9 @@ int64_t g_stem_pass_frames = kConvPassFrames;
 // default for u8 / bf16 frames; vfp_set_tuning(1, 0) selects the two-kernel path (always used for fp32 frames).
 int g_fused_stem = 2;
 int g_join_prefetch = 16;  // vfp_set_tuning key 5: column tiles of L2 prefetch distance in the join (0 = off)
+// Measured (10 000 clips): conv4 5.19 -> 4.9 ms on pairs; QKV 1.25 -> 1.91 and the out-projection 0.48 -> 0.64 ms (their K = 256
+// weight block is better kept resident in shared memory, gemm_bres_tcgen05_kernel), hence bit 1 is off by default.
+int g_pair_gemm = 1;        // key 15: bit 0 conv4, bit 1 QKV / out-projection on CTA pairs (gemm_pair_tcgen05_kernel)
 int g_ffn_mode = 1;         // key 14: 0 = two GEMM launches, 1 = fused feed-forward kernel on CTA pairs
 int g_conv_mcast = 0;       // key 13: bit 0 conv3, bit 1 conv4 run as CTA pairs that share the filter tile through multicast TMA
 int g_join_kernel = 2;      // key 10: 0 = the generic tile kernel, 1 = A-resident panel-major kernel, 2 = the same on CTA pairs (cta_group::2)
@@ -358,6 +362,7 @@ int vfp_set_tuning(int key, long long value) {
   if (key == 5 && value >= 0 && value <= 4096) { g_join_prefetch = (int)value; return 0; }
   if (key == 6 && value >= 0 && value <= 4096) { g_topk_prefetch = (int)value; return 0; }
   if (key == 3 && value >= 64 && value <= kConvPassFrames) { g_conv_pass_frames = value; return 0; }
+  if (key == 15 && value >= 0 && value <= 3) { g_pair_gemm = (int)value; return 0; }
   if (key == 14 && value >= 0 && value <= 1) { g_ffn_mode = (int)value; return 0; }
   if (key == 13 && value >= 0 && value <= 3) { g_conv_mcast = (int)value; return 0; }
   if (key == 10 && value >= 0 && value <= 2) { g_join_kernel = (int)value; return 0; }
@@ -609,7 +614,8 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
         make_tmap_rows_bf16(&a.tm_w1, a.w1, 4 * kDim, kDim, kDim, 256, 64) ||
         make_tmap_rows_bf16(&a.tm_w2, a.w2, kDim, 4 * kDim, 4 * kDim, 256, 64))
       return bail("tensor map encode failed (attention weights)");
-    if (make_tmap_rows_bf16(&a.tm_w1_ffn, a.w1, 4 * kDim, kDim, kDim, 128, 64) ||
+    if (make_tmap_rows_bf16(&a.tm_qkv_h, a.wqkv, 3 * kDim, kDim, kDim, 128, 64) || make_tmap_rows_bf16(&a.tm_o_h, a.wo, kDim, kDim, kDim, 128, 64) ||
+        make_tmap_rows_bf16(&a.tm_w1_ffn, a.w1, 4 * kDim, kDim, kDim, 128, 64) ||
         make_tmap_rows_bf16(&a.tm_w2_ffn, a.w2, kDim, 4 * kDim, 4 * kDim, 128, 64))
       return bail("tensor map encode failed (feed-forward weights)");
   }
@@ -759,7 +765,8 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     conv_taps_strided(&s, 2);
     EpiConvPool16::Params ep{};
     ep.bias = w->c4_b; ep.out_bf16 = feat_out; ep.frames = (int)F; ep.N = 256;
-    if (g_conv_mcast & 2) VFP_CUDA((launch_gemm<256, 64, 4, EpiConvPool16, 1, false, 2>(ta, w->tm_c4h, s, ep, st)));
+    if (g_pair_gemm & 1) VFP_CUDA((launch_gemm_pair<64, 6, EpiConvPool16>(ta, w->tm_c4h, s, ep, st)));   // CTA pairs: one M256 N256 UMMA per K step
+    else if (g_conv_mcast & 2) VFP_CUDA((launch_gemm<256, 64, 4, EpiConvPool16, 1, false, 2>(ta, w->tm_c4h, s, ep, st)));
     else VFP_CUDA((launch_gemm<256, 64, 4, EpiConvPool16>(ta, w->tm_c4, s, ep, st)));
     g_prof.mark(kStConv4, st);
   }
@@ -834,14 +841,16 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   };
   // bf16-output token GEMM, result written by the TMA unit (coalesced); act: 0 none, 2 gelu
   auto token_gemm_bf16 = [&](const __nv_bfloat16* A, int64_t M, int K, const CUtensorMap& tb, int N, const float* bias, int act,
-                             __nv_bfloat16* out) -> int {
+                             __nv_bfloat16* out, const CUtensorMap* tb_half = nullptr) -> int {
     CUtensorMap tma;
     if (make_tmap_rows_bf16(&tma, A, (uint64_t)M, (uint64_t)K, (uint64_t)K, 128, 64)) return fail("tensor map encode failed (tokens)");
     EpiBiasActTma<true>::Params ep{};
     if (make_tmap_out(&ep.tmap_out, out, (uint64_t)M, (uint64_t)N, true)) return fail("tensor map encode failed (token out)");
     ep.bias = bias; ep.N = N; ep.act = act;
     GemmShape s = plain_shape(M, N, K, 256, 64, 32);
-    if (K == 256) {
+    if (tb_half && (g_pair_gemm & 2)) {   // CTA pairs: one M256 N256 UMMA per K step, 32 KB per stage
+      VFP_CUDA((launch_gemm_pair<64, 6, EpiBiasActTma<true>>(tma, *tb_half, s, ep, st)));
+    } else if (K == 256) {
       VFP_CUDA((launch_gemm_bres<256, 64, 4, 4, EpiBiasActTma<true>>(tma, tb, s, ep, st)));
     } else {
       VFP_CUDA((launch_gemm<256, 64, 4, EpiBiasActTma<true>>(tma, tb, s, ep, st)));
@@ -873,11 +882,11 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     const AttnBlockWeights& a = w->attn[b];
     VFP_CUDA(launch_kernel(add_layernorm_bf16_kernel, dim3(ln_grid), dim3(256), 0, st, xa, b > 0 ? delta : nullptr, a.ln1_w, a.ln1_b, xn, (int)F));
     g_prof.mark(kStLayerNorm, st);
-    if (token_gemm_bf16(xn, F, kDim, a.tm_qkv, 3 * kDim, a.bqkv, 0, qkv)) return 1;
+    if (token_gemm_bf16(xn, F, kDim, a.tm_qkv, 3 * kDim, a.bqkv, 0, qkv, &a.tm_qkv_h)) return 1;
     g_prof.mark(kStQkv, st);
     VFP_CUDA(launch_kernel(attention_fa_kernel, dim3((unsigned)n_items), dim3(kAttThreads), kAttSmemBytes, st, qkv, att_items, att, (int)F));
     g_prof.mark(kStAttention, st);
-    if (token_gemm_bf16(att, F, kDim, a.tm_o, kDim, a.bo, 0, delta)) return 1;
+    if (token_gemm_bf16(att, F, kDim, a.tm_o, kDim, a.bo, 0, delta, &a.tm_o_h)) return 1;
     g_prof.mark(kStOutProj, st);
     VFP_CUDA(launch_kernel(add_layernorm_bf16_kernel, dim3(ln_grid), dim3(256), 0, st, xa, delta, a.ln2_w, a.ln2_b, xn, (int)F));
     g_prof.mark(kStLayerNorm, st);
