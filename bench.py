@@ -68,6 +68,7 @@ STAGE_FLOPS = {
     "out_proj_gemm": 4 * 2 * 256 * 256 * _T,
     "mlp1_gemm_gelu": 4 * 2 * 256 * 1024 * _T,
     "mlp2_gemm": 4 * 2 * 1024 * 256 * _T,
+    "ffn_fused": 4 * 2 * 2 * 256 * 1024 * _T,                   # both MLP GEMMs in one kernel
     "pool_logits_gemm": 2 * 256 * 256 * _T,
 }
 # algorithmic HBM bytes per clip of the stages whose binding roofline is memory, not the tensor pipe

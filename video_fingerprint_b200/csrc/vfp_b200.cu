@@ -52,12 +52,12 @@ constexpr float kBnEps = 1e-5f;
 // ---------------------------------------------------------------------------------------------
 enum Stage : int {
   kStConv1 = 0, kStConv2, kStConv3, kStConv4, kStTokEmbed, kStTemporalConv, kStLayerNorm, kStQkv, kStAttention,
-  kStOutProj, kStMlp1, kStMlp2, kStPoolGemm, kStPool, kStFinal, kStMisc, kStStemFused, kNumStages
+  kStOutProj, kStMlp1, kStMlp2, kStPoolGemm, kStPool, kStFinal, kStMisc, kStStemFused, kStFfn, kNumStages
 };
 const char* const kStageNames[kNumStages] = {"conv1_stem", "conv2_igemm", "conv3_igemm", "conv4_igemm_pool", "token_embed_gemm",
                                              "temporal_conv", "layernorm", "qkv_gemm", "attention", "out_proj_gemm",
                                              "mlp1_gemm_gelu", "mlp2_gemm", "pool_logits_gemm", "temporal_pool",
-                                             "final_projection", "misc", "stem_fused"};
+                                             "final_projection", "misc", "stem_fused", "ffn_fused"};
 struct Profiler {
   bool enabled = false;
   std::vector<cudaEvent_t> pool;
@@ -903,7 +903,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
       const int grid = 2 * std::min(fp.pair_tiles, persistent_grid() / 2);
       VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(ffn_pair_kernel<5>), FfnSmem<5>::kTotal));
       VFP_CUDA(launch_kernel_cluster(2, ffn_pair_kernel<5>, dim3(grid), dim3(kFfnThreads), FfnSmem<5>::kTotal, st, fp));
-      g_prof.mark(kStMlp1, st);   // reported under the up-projection's stage name; mlp2_gemm stays 0
+      g_prof.mark(kStFfn, st);
     }
   }
   // close the last block's residual and make the bf16 copy the pooling GEMM reads
