@@ -20,7 +20,9 @@
 //               16 KB slots, in exactly the order the issuer consumes them; byte counts land on the LEADER's barriers
 //   warp 1      TMEM allocation (512 columns: D1 256 | D2 256); in the leader CTA (cluster rank 0) also the UMMA issuer,
 //               whose commits are multicast to both CTAs' barriers
-//   warps 2-9   activation / output warps (both CTAs): TMEM lane quarter = warp % 4, column half = (warp - 2) / 4
+//   warps 2-17  activation / output warps (both CTAs): TMEM lane quarter = warp % 4, column quarter = (warp - 2) / 4.
+//               Sixteen of them: the activation phase is bound by the MUFU pipe (one tanh per element, 2 048 cycles per chunk)
+//               and the FMA pipe (~2 300), with eight warps it took 4 000 cycles (cycle trace) and set the kernel's pace
 // D1 and H are single buffers: the issuer's order G1(n+1), G2(n) puts a whole GEMM between a buffer's last read and its next
 // write, which is when the activation warps drain D1 / refill H.
 #pragma once
@@ -32,7 +34,8 @@ namespace vfp {
 constexpr int kFfnHidden = 1024;
 constexpr int kFfnChunk = 256;
 constexpr int kFfnChunks = kFfnHidden / kFfnChunk;
-constexpr int kFfnThreads = 64 + 256;
+constexpr int kFfnActWarps = 16;                     // four per TMEM lane quarter: 64 hidden / 64 output columns each
+constexpr int kFfnThreads = 64 + 32 * kFfnActWarps;
 
 // development trace (-DVFP_FFN_TRACE): block 0 records (tag, clock) pairs of its producer, issuer and first activation warp
 #ifdef VFP_FFN_TRACE
@@ -60,9 +63,9 @@ struct FfnParams {
   alignas(64) CUtensorMap tmap_x;    // xn [M][256] bf16, box 128 rows x 64 cols, SWIZZLE_128B
   alignas(64) CUtensorMap tmap_w1;   // W1 [1024][256] bf16 K-major, box 128 rows x 64 cols
   alignas(64) CUtensorMap tmap_w2;   // W2 [256][1024] bf16 K-major, box 128 rows x 64 cols
+  alignas(64) CUtensorMap tmap_out;  // delta [M][256] bf16, box 32 x 32, SWIZZLE_64B
   const float* b1;                   // [1024]
   const float* b2;                   // [256]
-  __nv_bfloat16* out;                // delta [M][256] bf16
   int M;
   int pair_tiles;                    // ceil(M / 256)
 };
@@ -104,6 +107,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_pair_kernel(const __grid_c
     tma_prefetch_desc(&p.tmap_x);
     tma_prefetch_desc(&p.tmap_w1);
     tma_prefetch_desc(&p.tmap_w2);
+    tma_prefetch_desc(&p.tmap_out);
     for (int i = 0; i < SLOTS; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -111,11 +115,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_pair_kernel(const __grid_c
     mbar_init(a0_full, 1);
     mbar_init(a0_empty, 1);
     mbar_init(d1_full, 1);
-    mbar_init(d1_empty, 16);
-    mbar_init(h_full, 16);
+    mbar_init(d1_empty, 2 * kFfnActWarps);
+    mbar_init(h_full, 2 * kFfnActWarps);
     mbar_init(h_empty, 1);
     mbar_init(d2_full, 1);
-    mbar_init(d2_empty, 16);
+    mbar_init(d2_empty, 2 * kFfnActWarps);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -232,46 +236,58 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_pair_kernel(const __grid_c
   } else {
     // ------------------------------ activation + output warps (both CTAs) ------------------------------
     const int q = warp & 3;                 // TMEM lane quarter
-    const int ch = (warp - 2) >> 2;         // column half: hidden columns 128 ch .. of the chunk / output columns 128 ch ..
+    const int cq = (warp - 2) >> 2;         // column quarter: hidden columns 64 cq .. of the chunk / output columns 64 cq ..
     const int row = q * 32 + lane;          // token row inside this CTA's tile
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     uint32_t d1f_ph = 0, he_ph = 0, d2f_ph = 0;
     FFN_TRACE_DECL(1);
     const uint32_t d1_empty_leader = mapa_u32(d1_empty, 0), h_full_leader = mapa_u32(h_full, 0), d2_empty_leader = mapa_u32(d2_empty, 0);
     // hidden chunk layout (A operand of GEMM2): K block = 64 hidden columns = one 128-byte row per token, 16-byte pieces
-    // XOR-swizzled with the row index (SWIZZLE_128B); this warp's 128 columns are K blocks 2 ch and 2 ch + 1
-    uint8_t* h_row = hbuf + (2 * ch) * 16384 + row * 128;
+    // XOR-swizzled with the row index (SWIZZLE_128B); this warp's 64 columns are K block cq
+    uint8_t* h_row = hbuf + cq * 16384 + row * 128;
     const uint32_t sw = (uint32_t)(row & 7);
+    // output staging: once GEMM2 of a tile's last chunk has completed the hidden buffer is free; every warp stages its
+    // 32 rows x 64 columns there (two 2 KB chunks of 32 x 32 bf16, SWIZZLE_64B) and hands them to the TMA unit
+    uint8_t* stage = hbuf + (warp - 2) * 4096;
 
-    auto output_tile = [&](int tile) {   // delta = D2 + b2 -> bf16; this thread's 128 columns of its row = 256 contiguous bytes
+    auto output_tile = [&](int tile) {   // delta = D2 + b2 -> bf16 -> staging -> TMA store
       mbar_wait(d2_full, d2f_ph);
       d2f_ph ^= 1;
       tc_fence_after();
-      const long long grow = ((long long)tile * 2 + crank) * 128 + row;
-      __nv_bfloat16* orow = p.out + grow * 256 + ch * 128;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + 256 + ch * 128 + c * 32, v);
-        tmem_ld_wait();
-        const float* bias = sbias + kFfnHidden + ch * 128 + c * 32;
-        if (grow < p.M) {
 #pragma unroll
-          for (int piece = 0; piece < 4; ++piece) {
-            const float4 ba = *reinterpret_cast<const float4*>(bias + 8 * piece);
-            const float4 bc = *reinterpret_cast<const float4*>(bias + 8 * piece + 4);
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[8 * piece + 0]) + ba.x, __uint_as_float(v[8 * piece + 1]) + ba.y);
-            o.y = pack_bf16x2(__uint_as_float(v[8 * piece + 2]) + ba.z, __uint_as_float(v[8 * piece + 3]) + ba.w);
-            o.z = pack_bf16x2(__uint_as_float(v[8 * piece + 4]) + bc.x, __uint_as_float(v[8 * piece + 5]) + bc.y);
-            o.w = pack_bf16x2(__uint_as_float(v[8 * piece + 6]) + bc.z, __uint_as_float(v[8 * piece + 7]) + bc.w);
-            *reinterpret_cast<uint4*>(orow + c * 32 + piece * 8) = o;
-          }
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_addr + 256 + cq * 64 + c * 32, v);
+        tmem_ld_wait();
+        const float* bias = sbias + kFfnHidden + cq * 64 + c * 32;
+        uint8_t* r0 = stage + c * 2048 + lane * 64;
+        const int s64 = (lane >> 1) & 3;
+#pragma unroll
+        for (int piece = 0; piece < 4; ++piece) {
+          const float4 ba = *reinterpret_cast<const float4*>(bias + 8 * piece);
+          const float4 bc = *reinterpret_cast<const float4*>(bias + 8 * piece + 4);
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[8 * piece + 0]) + ba.x, __uint_as_float(v[8 * piece + 1]) + ba.y);
+          o.y = pack_bf16x2(__uint_as_float(v[8 * piece + 2]) + ba.z, __uint_as_float(v[8 * piece + 3]) + ba.w);
+          o.z = pack_bf16x2(__uint_as_float(v[8 * piece + 4]) + bc.x, __uint_as_float(v[8 * piece + 5]) + bc.y);
+          o.w = pack_bf16x2(__uint_as_float(v[8 * piece + 6]) + bc.z, __uint_as_float(v[8 * piece + 7]) + bc.w);
+          *reinterpret_cast<uint4*>(r0 + ((piece ^ s64) << 4)) = o;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(d2_empty_leader);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        const int grow0 = (tile * 2 + (int)crank) * 128 + q * 32;
+        tma_store_2d(&p.tmap_out, stage, cq * 64, grow0);          // rows past M are clipped by the tensor map
+        tma_store_2d(&p.tmap_out, stage + 2048, cq * 64 + 32, grow0);
+        tma_store_commit();
+        tma_store_wait_read<0>();   // the staging bytes are about to be overwritten by the next hidden chunk
+      }
+      // every warp's stores must have been read before ANY warp writes the hidden buffer again
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kFfnActWarps) : "memory");
     };
 
     for (int n = 0; n < n_chunks; ++n) {
@@ -281,30 +297,27 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_pair_kernel(const __grid_c
       d1f_ph ^= 1;
       tc_fence_after();
       if (warp == 2 && lane == 0) FFN_TRACE(201);
-      uint32_t packed[64];
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {   // two 64-column halves of this warp's 128 columns (= K blocks 2 ch + hh)
+      uint32_t packed[32];
+      {
         uint32_t va[32], vb[32];
-        tmem_ld_32x32(lane_addr + ch * 128 + hh * 64, va);
-        tmem_ld_32x32(lane_addr + ch * 128 + hh * 64 + 32, vb);
+        tmem_ld_32x32(lane_addr + cq * 64, va);
+        tmem_ld_32x32(lane_addr + cq * 64 + 32, vb);
         tmem_ld_wait();
-        if (warp == 2 && lane == 0) FFN_TRACE(202 + hh);
-        if (hh == 1) {   // D1 is in registers: GEMM1 of the next chunk may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(d1_empty_leader);
-        }
+        if (warp == 2 && lane == 0) FFN_TRACE(203);
+        tc_fence_before();   // D1 is in registers: GEMM1 of the next chunk may overwrite it
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(d1_empty_leader);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t(&v)[32] = cc ? vb : va;
-          const float* bias = sbias + c * kFfnChunk + ch * 128 + hh * 64 + cc * 32;
+          const float* bias = sbias + c * kFfnChunk + cq * 64 + cc * 32;
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 bb = *reinterpret_cast<const float4*>(bias + i);
             const float2 y0 = gelu_erf2(fadd2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), make_float2(bb.x, bb.y)));
             const float2 y1 = gelu_erf2(fadd2(make_float2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), make_float2(bb.z, bb.w)));
-            packed[hh * 32 + cc * 16 + i / 2] = pack_bf16x2(y0.x, y0.y);
-            packed[hh * 32 + cc * 16 + i / 2 + 1] = pack_bf16x2(y1.x, y1.y);
+            packed[cc * 16 + i / 2] = pack_bf16x2(y0.x, y0.y);
+            packed[cc * 16 + i / 2 + 1] = pack_bf16x2(y1.x, y1.y);
           }
         }
       }
@@ -317,17 +330,16 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_pair_kernel(const __grid_c
       he_ph ^= 1;
       if (warp == 2 && lane == 0) FFN_TRACE(206);
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-        for (int piece = 0; piece < 8; ++piece)
-          *reinterpret_cast<uint4*>(h_row + hh * 16384 + ((piece ^ sw) << 4)) =
-              make_uint4(packed[hh * 32 + 4 * piece], packed[hh * 32 + 4 * piece + 1], packed[hh * 32 + 4 * piece + 2], packed[hh * 32 + 4 * piece + 3]);
+      for (int piece = 0; piece < 8; ++piece)
+        *reinterpret_cast<uint4*>(h_row + ((piece ^ sw) << 4)) =
+            make_uint4(packed[4 * piece], packed[4 * piece + 1], packed[4 * piece + 2], packed[4 * piece + 3]);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(h_full_leader);
       if (warp == 2 && lane == 0) FFN_TRACE(207);
     }
     if (n_chunks > 0) output_tile(pair + (my_tiles - 1) * n_pairs);
+    if (lane == 0) tma_store_wait_read<0>();
   }
 
   __syncwarp();

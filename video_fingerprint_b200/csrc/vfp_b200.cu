@@ -899,7 +899,8 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
       FfnParams fp{};
       if (make_tmap_rows_bf16(&fp.tmap_x, xn, (uint64_t)F, kDim, kDim, 128, 64)) return fail("tensor map encode failed (feed-forward)");
       fp.tmap_w1 = a.tm_w1_ffn; fp.tmap_w2 = a.tm_w2_ffn;
-      fp.b1 = a.b1; fp.b2 = a.b2; fp.out = delta; fp.M = (int)F; fp.pair_tiles = (int)((F + 255) / 256);
+      if (make_tmap_out(&fp.tmap_out, delta, (uint64_t)F, kDim, true)) return fail("tensor map encode failed (feed-forward out)");
+      fp.b1 = a.b1; fp.b2 = a.b2; fp.M = (int)F; fp.pair_tiles = (int)((F + 255) / 256);
       const int grid = 2 * std::min(fp.pair_tiles, persistent_grid() / 2);
       VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(ffn_pair_kernel<5>), FfnSmem<5>::kTotal));
       VFP_CUDA(launch_kernel_cluster(2, ffn_pair_kernel<5>, dim3(grid), dim3(kFfnThreads), FfnSmem<5>::kTotal, st, fp));
