@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "conv1_kernel.cuh"
+#include "conv3_ts_kernel.cuh"
 #include "ffn_kernel.cuh"
 #include "gemm_launch.cuh"
 #include "join_kernels.cuh"
@@ -258,6 +259,7 @@ int g_fused_stem = 2;
 int g_join_prefetch = 16;  // vfp_set_tuning key 5: column tiles of L2 prefetch distance in the join (0 = off)
 // Measured (10 000 clips): conv4 5.19 -> 4.9 ms on pairs; QKV 1.25 -> 1.91 and the out-projection 0.48 -> 0.64 ms (their K = 256
 // weight block is better kept resident in shared memory, gemm_bres_tcgen05_kernel), hence bit 1 is off by default.
+int g_conv3_ts = 1;         // key 16: conv3 with its filters in tensor memory (TS-mode UMMAs) instead of the generic SWAP kernel
 int g_pair_gemm = 1;        // key 15: bit 0 conv4, bit 1 QKV / out-projection on CTA pairs (gemm_pair_tcgen05_kernel)
 int g_ffn_mode = 1;         // key 14: 0 = two GEMM launches, 1 = fused feed-forward kernel on CTA pairs
 int g_conv_mcast = 0;       // key 13: bit 0 conv3, bit 1 conv4 run as CTA pairs that share the filter tile through multicast TMA
@@ -362,6 +364,7 @@ int vfp_set_tuning(int key, long long value) {
   if (key == 5 && value >= 0 && value <= 4096) { g_join_prefetch = (int)value; return 0; }
   if (key == 6 && value >= 0 && value <= 4096) { g_topk_prefetch = (int)value; return 0; }
   if (key == 3 && value >= 64 && value <= kConvPassFrames) { g_conv_pass_frames = value; return 0; }
+  if (key == 16 && value >= 0 && value <= 1) { g_conv3_ts = (int)value; return 0; }
   if (key == 15 && value >= 0 && value <= 3) { g_pair_gemm = (int)value; return 0; }
   if (key == 14 && value >= 0 && value <= 1) { g_ffn_mode = (int)value; return 0; }
   if (key == 13 && value >= 0 && value <= 3) { g_conv_mcast = (int)value; return 0; }
@@ -744,6 +747,15 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
   {  // conv3: 16x16x64 -> 8x8x128 through a stride-2 box, tile = 2 frames. (A weight-resident variant - launch_gemm_bres<128, 64, 3, 9>,
      // all nine filter blocks in shared memory, M = 128 pixels - measured 2.01 ms vs 1.25 ms per 131 072 frames: the kernel is
      // bound by the nine-fold L2 -> SM re-read of the input pixels, not by the weights.)
+    if (g_conv3_ts) {   // filters in tensor memory, three frames per tile (conv3_ts_kernel.cuh)
+      Conv3Params cp{};
+      if (make_tmap_nhwc_bf16(&cp.tmap_in, c2a, F, 16, 16, 64, 64, 8, 8, kC3Frames, 2) || make_tmap_out(&cp.tmap_out, c3a, (uint64_t)F * 64, 128, true))
+        return fail("tensor map encode failed (conv3)");
+      cp.w = w->c3_w; cp.bias = w->c3_b; cp.n_tiles = (int)((F + kC3Frames - 1) / kC3Frames);
+      VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(conv3_ts_kernel<7>), Conv3Smem<7>::kTotal));
+      VFP_CUDA(launch_kernel(conv3_ts_kernel<7>, dim3(std::min(cp.n_tiles, persistent_grid())), dim3(kC3Threads), Conv3Smem<7>::kTotal, st, cp));
+      g_prof.mark(kStConv3, st);
+    } else {
     if (make_tmap_nhwc_bf16(&ta, c2a, F, 16, 16, 64, 64, 8, 8, 2, 2)) return fail("tensor map encode failed (conv3)");
     GemmShape s{};
     s.m_tiles = (int)((F + 1) / 2); s.n_tiles = 1; s.k_blocks = 9; s.group_m = 16; s.a_conv = 1;
@@ -756,6 +768,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     if (g_conv_mcast & 1) VFP_CUDA((launch_gemm<128, 64, 4, EpiConvTransposedTma, 2, true, 2>(ta, w->tm_c3h, s, ep, st)));
     else VFP_CUDA((launch_gemm<128, 64, 4, EpiConvTransposedTma, 2, true>(ta, w->tm_c3, s, ep, st)));
     g_prof.mark(kStConv3, st);
+    }
   }
   {  // conv4: 8x8x128 -> 4x4x256 + ReLU + global average pool, tile = 8 frames
     if (make_tmap_nhwc_bf16(&ta, c3a, F, 8, 8, 128, 64, 4, 4, 8, 2)) return fail("tensor map encode failed (conv4)");
