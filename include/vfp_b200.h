@@ -161,11 +161,17 @@ int vfp_profile_num_stages(void);
 const char* vfp_profile_stage_name(int i);
 int vfp_profile_read(double* stage_ms, int n_stages, uint64_t* launches, int reset);
 
-/* Tuning knobs for experiments (process-wide). key 0: frames per conv1+conv2 stem pass of the
- * unfused path (default 16384 = the conv pass, >= 64); key 1: conv1+conv2 stem: 2 = fused, conv1 as TS-mode tcgen05 UMMA (default
- * for u8 / bf16 frames), 1 = fused with conv1 on mma.sync, 0 = two kernels (always used for fp32 frames); key 2: 1 = hang diagnosis
- * mode (see vfp_debug_hang_log), 0 = watchdog traps (default); key 3: frames per conv pass (64..16384, default 16384);
- * key 5 / key 6: L2 prefetch distance in column tiles of the join / the top-k screen for databases larger than L2 (0 = off). */
+/* Tuning knobs for experiments (process-wide; defaults in parentheses). key 0: frames per conv1+conv2 pass of the two-kernel
+ * stem (16384, >= 64); key 1: conv1+conv2 stem: 2 = fused kernel, conv1 as TS-mode tcgen05 UMMA (default for u8 / bf16 frames),
+ * 0 = two kernels (always used for fp32 frames); key 2: 1 = hang diagnosis mode (see vfp_debug_hang_log), 0 = watchdog traps
+ * (default); key 3: frames per conv pass (64..16384, default 16384); key 5 / key 6: L2 prefetch distance in column tiles of the
+ * one-CTA join kernel / the top-k screen for databases larger than L2 (0 = off); key 7: programmatic dependent launch between
+ * the forward's kernels (0); key 8: cap on the CTAs of persistent kernels (0 = one per SM); key 9: conv passes in flight on
+ * separate streams (1); key 10: join kernel, 0 = one CTA per tile, 1 = A-resident, 2 = A-resident CTA pairs (2); key 11:
+ * self joins compute the upper triangle and mirror the pairs (1); key 12: join panel width in column tiles (512); key 13:
+ * TMA multicast of the conv3 / conv4 filter tile across a CTA pair, bit mask (0); key 14: 1 = both MLP linears in one kernel (1);
+ * key 15: CTA-pair GEMM, bit 0 conv4, bit 1 QKV / out-projection (1); key 16: conv3 with its filters in tensor memory (1).
+ * Every setting produces the same results up to fp32 summation order (scripts/dev_tuning_parity.py). */
 int vfp_set_tuning(int key, long long value);
 
 /* Reads and clears the device-side error word set by a kernel watchdog (0 = none). Synchronises. */

@@ -7,7 +7,6 @@ are garbage, only the time matters). Build the variants next to the real library
       nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC \
            -DVFP_STEM_KNOCKOUT=$m -shared -o build/libvfp_ko$m.so video_fingerprint_b200/csrc/vfp_b200.cu; done
     VFP_B200_LIB=build/libvfp_ko127.so PYTHONPATH=. python scripts/dev_knockout.py 1024
-    PYTHONPATH=. python scripts/dev_knockout.py 1024 1      # stem mode 1 (conv1 on mma.sync) for comparison
 """
 import ctypes as C
 import sys

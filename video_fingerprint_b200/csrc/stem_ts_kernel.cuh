@@ -1,5 +1,5 @@
 // Fused frame-encoder stem, all-tcgen05 version: conv1 (3->32, k5 s2) runs on the 5th-gen tensor cores too, as a
-// "TS" UMMA whose A operand (the im2col rows) lives in TENSOR MEMORY. stem_fused_kernel.cuh computes conv1 with
+// "TS" UMMA whose A operand (the im2col rows) lives in TENSOR MEMORY. The round-1 kernel computed conv1 with
 // mma.sync: 1360 HMMA.16816 per frame keep the legacy tensor path busy for ~2750 cycles per frame (8.1 cycles per HMMA and
 // SM sub-partition, profiles/r01_microbench_tensor_pipe.txt), during which conv2's UMMAs cannot run (and vice versa).
 //
@@ -16,7 +16,7 @@
 //   GEMM per tile: M = 128 rows = 4 cell rows x 16 cells x 2 sub-rows (sh), N = 64 = (sw, 32 channels), K = 128
 //   -> 8 UMMAs (M128 N64 K16, TS) of ~49 cycles; 4 tiles per frame = 1570 cycles instead of 2750.
 // The accumulator row of thread (cell, sh) is exactly the 2 x 64 bytes conv2's A-operand buffers AL0 / AL1 need from it
-// (see stem_fused_kernel.cuh for those buffers; conv2's UMMA schedule, weights and epilogue are unchanged).
+// (see stem_common.cuh for those buffers and conv2's UMMA schedule).
 //
 // What bounds this kernel is the serial instruction stream of each role, not a pipe (scripts/dev_knockout.py, and
 // tests/cuda/microbench_handoff.cu: an mbarrier hand-off costs 100-250 cycles): with every load, store and UMMA removed
@@ -36,7 +36,7 @@
 // TMEM (512 columns), everything double buffered: conv2 accumulators 2 x 128 (columns 0-63: all unshifted taps, kw = 1 and
 // kw = 2, summed by the tensor core; 64-127: the kw = 0 taps the epilogue shifts by one cell), conv1 A 2 x 64, conv1 D 2 x 64.
 #pragma once
-#include "stem_fused_kernel.cuh"
+#include "stem_common.cuh"
 
 namespace vfp {
 
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
         mbar_wait_relaxed(&c1_full[b], ph);
         tc_fence_after();
         if (lane == 0) {
-          // the four tap groups of stem_fused_kernel, but the unshifted ones share an accumulator: columns 0-63 collect the
+          // the four tap groups of stem_common.cuh, the unshifted ones sharing an accumulator: columns 0-63 collect the
           // kw = 1 taps (N = 64 UMMAs on AL0) AND the kw = 2 taps (first half of the stacked N = 128 UMMAs on AL1), columns
           // 64-127 the kw = 0 taps. Descriptor arithmetic in 16-byte units: K step 2, buffer cell row 128, weight block 512
           const uint32_t d_acc = tmem_base + kTsColAcc + b * 128;

@@ -18,7 +18,6 @@
 #include "metrics_kernels.cuh"
 #include "model3d_kernels.cuh"
 #include "preprocess_kernels.cuh"
-#include "stem_fused_kernel.cuh"
 #include "stem_ts_kernel.cuh"
 #include "token_kernels.cuh"
 #include "topk_kernels.cuh"
@@ -118,7 +117,6 @@ struct vfp_weights {
   std::vector<void*> allocs;
   // frame encoder
   uint32_t* c1_wpack = nullptr;
-  uint32_t* c1_wpack_perm = nullptr;  // same fragments with the output channels permuted for the fused stem kernel
   float* c1_bias = nullptr;
   __nv_bfloat16 *c2_w = nullptr, *c3_w = nullptr, *c4_w = nullptr;
   float *c2_b = nullptr, *c3_b = nullptr, *c4_b = nullptr;
@@ -252,8 +250,8 @@ int64_t g_conv_pass_frames = kConvPassFrames;
 // conv1+conv2 sub-pass. Measured on B200 (10k x 64-frame clips): 512 -> 71.3 ms/step, 1024 -> 62.9, 2048 -> 60.7,
 // 4096 -> 58.9, 16384 -> 55.8: short L2-sized sub-passes lose more to small launches than they save in HBM traffic.
 int64_t g_stem_pass_frames = kConvPassFrames;
-// conv1+conv2 in one kernel (stem_fused_kernel.cuh: conv1's output stays in shared memory as conv2's UMMA operand).
-// Measured on B200 (10k x 64-frame clips): 18.4 ms vs 13.4 + 12.9 ms for the two HBM-bound kernels, so it is the
+// conv1+conv2 in one kernel (stem_ts_kernel.cuh: conv1's output stays in shared memory as conv2's UMMA operand).
+// Measured on B200 (10k x 64-frame clips): 13.3 ms vs 13.4 + 12.9 ms for the two HBM-bound kernels, so it is the
 // default for u8 / bf16 frames; vfp_set_tuning(1, 0) selects the two-kernel path (always used for fp32 frames).
 int g_fused_stem = 2;
 int g_join_prefetch = 16;  // vfp_set_tuning key 5: column tiles of L2 prefetch distance in the join (0 = off)
@@ -360,7 +358,7 @@ int vfp_device_sm_count(void) {
 
 int vfp_set_tuning(int key, long long value) {
   if (key == 0 && value >= 64) { g_stem_pass_frames = value; return 0; }
-  if (key == 1 && value >= 0 && value <= 2) { g_fused_stem = (int)value; return 0; }
+  if (key == 1 && (value == 0 || value == 2)) { g_fused_stem = (int)value; return 0; }
   if (key == 5 && value >= 0 && value <= 4096) { g_join_prefetch = (int)value; return 0; }
   if (key == 6 && value >= 0 && value <= 4096) { g_topk_prefetch = (int)value; return 0; }
   if (key == 3 && value >= 64 && value <= kConvPassFrames) { g_conv_pass_frames = value; return 0; }
@@ -464,26 +462,24 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
       const int kw = k / 3, c = k % 3;
       return cw[((co * 3 + c) * 5 + kh) * 5 + kw] * bn.scale[co];
     };
-    // perm = 0: column g of n-tile nt is channel nt*8 + g (stand-alone conv1 kernel); perm = 1: channel
-    // 8*(g>>1) + 2*nt + (g&1), which leaves every thread of the fused stem kernel with 8 consecutive channels
-    std::vector<uint32_t> pack(5 * 4 * 32 * 2), pack_perm(5 * 4 * 32 * 2);
-    for (int perm = 0; perm < 2; ++perm)
-      for (int kh = 0; kh < 5; ++kh)
-        for (int nt = 0; nt < 4; ++nt)
-          for (int lane = 0; lane < 32; ++lane) {
-            const int g = lane >> 2, tig = lane & 3, co = perm ? 8 * (g >> 1) + 2 * nt + (g & 1) : nt * 8 + g;
-            for (int r = 0; r < 2; ++r) {
-              const int k0 = 2 * tig + 8 * r;
-              const __nv_bfloat16 lo = __float2bfloat16(wk(co, kh, k0)), hi = __float2bfloat16(wk(co, kh, k0 + 1));
-              uint16_t l16, h16;
-              memcpy(&l16, &lo, 2);
-              memcpy(&h16, &hi, 2);
-              (perm ? pack_perm : pack)[((kh * 4 + nt) * 32 + lane) * 2 + r] = (uint32_t)l16 | ((uint32_t)h16 << 16);
-            }
+    // column g of n-tile nt is channel nt*8 + g
+    std::vector<uint32_t> pack(5 * 4 * 32 * 2);
+    for (int kh = 0; kh < 5; ++kh)
+      for (int nt = 0; nt < 4; ++nt)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int g = lane >> 2, tig = lane & 3, co = nt * 8 + g;
+          for (int r = 0; r < 2; ++r) {
+            const int k0 = 2 * tig + 8 * r;
+            const __nv_bfloat16 lo = __float2bfloat16(wk(co, kh, k0)), hi = __float2bfloat16(wk(co, kh, k0 + 1));
+            uint16_t l16, h16;
+            memcpy(&l16, &lo, 2);
+            memcpy(&h16, &hi, 2);
+            pack[((kh * 4 + nt) * 32 + lane) * 2 + r] = (uint32_t)l16 | ((uint32_t)h16 << 16);
           }
+        }
     std::vector<float> bias(32);
     for (int co = 0; co < 32; ++co) bias[co] = cb[co] * bn.scale[co] + bn.shift[co];
-    if (upload(w, pack, &w->c1_wpack) || upload(w, pack_perm, &w->c1_wpack_perm) || upload(w, bias, &w->c1_bias)) return bail("");
+    if (upload(w, pack, &w->c1_wpack) || upload(w, bias, &w->c1_bias)) return bail("");
     // stem_ts_kernel.cuh: an A row is a horizontal pair of output pixels (sw = 0, 1) of output row oh; per filter row kh it
     // holds 24 consecutive HWC values starting at pixel 4cx-3 channel 1: k = kh*24 + 2 + 3*p + ci is pixel 4cx-2+p, channel
     // ci. Output pixel ow = 2cx + sw reads pixels 4cx + 2sw - 2 + kw, i.e. p = 2sw + kw. Everything else is zero.
@@ -522,7 +518,7 @@ int vfp_weights_create(const vfp_tensor_desc* tensors, int n_tensors, vfp_weight
       bf[co] = cb[co] * bn.scale[co] + bn.shift[co];
     }
     if (upload(w, to_bf16(wf), &w->c2_w) || upload(w, bf, &w->c2_b)) return bail("");
-    // fused stem kernel (stem_fused_kernel.cuh), five K blocks of 64 = [half 0: 32 ch | half 1: 32 ch], per block and
+    // fused stem kernel (stem_common.cuh), five K blocks of 64 = [half 0: 32 ch | half 1: 32 ch], per block and
     // half the (kh, kw) tap it holds (-1 = zero):
     //   blk0 G_A (AL0, dh=0):  (1,1) | (2,1)      blk1 G_B (AL1, dh=0): (2,2) | (1,2)      blk2 G_C (AL1, dh=0, shifted): (2,0) | (1,0)
     //   blk3 G_E | G_D (dh=-1): (0,2) | (0,1)     blk4 G_F (dh=-1, shifted): (0,0) | zero
@@ -692,7 +688,7 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
   CUtensorMap ta;
   // the fused stem streams raw frame planes with 16-byte bulk copies; fp32 frames (48 KB) do not fit its smem ring
   const bool fused = g_fused_stem && frame_dtype != VFP_FRAME_F32 && (reinterpret_cast<uintptr_t>(frames) & 15) == 0;
-  if (fused && g_fused_stem == 2) {
+  if (fused) {
     StemTsParams sp{};
     sp.tmap_w2 = w->tm_c2f;
     sp.tmap_w1 = w->tm_c1ts;
@@ -703,17 +699,6 @@ int encode_frames_pass(const vfp_weights* w, const uint8_t* frames, int frame_dt
     g_prof.launches += 1;
     const int grid = (int)std::min<int64_t>(F, persistent_grid());
     VFP_CUDA(launch_kernel(stem_ts_kernel, dim3(grid), dim3(kStemThreads), StemTsSmem::kTotal, st, sp));
-    g_prof.mark(kStStemFused, st);
-  } else if (fused) {
-    StemParams sp{};
-    sp.tmap_w = w->tm_c2f;
-    if (make_tmap_out(&sp.tmap_out, c2a, (uint64_t)F * 256, 64, true)) return fail("tensor map encode failed (stem out)");
-    sp.frames = frames; sp.frame_dtype = frame_dtype; sp.n_frames = F;
-    sp.c1_wpack = w->c1_wpack_perm; sp.c1_bias = w->c1_bias; sp.c2_bias = w->c2_b;
-    VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(stem_fused_kernel), StemSmem::kTotal));
-    g_prof.launches += 1;
-    const int grid = (int)std::min<int64_t>(F, device_sm_count());
-    stem_fused_kernel<<<grid, kStemThreads, StemSmem::kTotal, st>>>(sp);
     g_prof.mark(kStStemFused, st);
   }
   for (int64_t s0 = 0; s0 < F && !fused; s0 += g_stem_pass_frames) {
