@@ -352,7 +352,8 @@ def bench_cfg4_join(vfp, world, rank, dev, peaks, n_total: int, reps: int):
     def step():
         res["out"] = sharding.sharded_threshold_join_device(local, 0.95)
 
-    step()
+    for _ in range(3):    # warm-up: the first call pays NCCL's connection set-up and the allocator's first big blocks (4 GPUs: 90 ms
+        step()            # against 54 ms in steady state, scripts/dev_sharded_join_phases.py)
     ms = timed_ms(step, reps, world, dev)
     i, j, s, _ = res["out"]
     pairs = int(sum_over_ranks(float(i.numel()), world, dev))
@@ -590,7 +591,7 @@ def run_ours(args):
         return out
 
     cfg3 = guarded(bench_cfg3_varlen, vfp, model, world, rank, dev, peaks, args.cfg3_videos, 3) if not args.no_cfg3 else None
-    cfg4 = guarded(bench_cfg4_join, vfp, world, rank, dev, peaks, args.cfg4_rows, 2) if not args.no_cfg4 else None
+    cfg4 = guarded(bench_cfg4_join, vfp, world, rank, dev, peaks, args.cfg4_rows, 3) if not args.no_cfg4 else None
     cfg5 = guarded(bench_cfg5_topk, vfp, world, rank, dev, peaks, args.cfg5_db, args.cfg5_q, 10, 2) if not args.no_cfg5 else None
 
     if rank == 0:
