@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "conv1_kernel.cuh"
+#include "attention_tc_kernel.cuh"
 #include "conv3_ts_kernel.cuh"
 #include "ffn_kernel.cuh"
 #include "gemm_launch.cuh"
@@ -257,6 +258,7 @@ int g_fused_stem = 2;
 int g_join_prefetch = 16;  // vfp_set_tuning key 5: column tiles of L2 prefetch distance in the join (0 = off)
 // Measured (10 000 clips): conv4 5.19 -> 4.9 ms on pairs; QKV 1.25 -> 1.91 and the out-projection 0.48 -> 0.64 ms (their K = 256
 // weight block is better kept resident in shared memory, gemm_bres_tcgen05_kernel), hence bit 1 is off by default.
+int g_attention_tc = 1;    // key 17: attention on tcgen05 (attention_tc_kernel.cuh) instead of the mma.sync kernel
 int g_conv3_ts = 1;         // key 16: conv3 with its filters in tensor memory (TS-mode UMMAs) instead of the generic SWAP kernel
 int g_pair_gemm = 1;        // key 15: bit 0 conv4, bit 1 QKV / out-projection on CTA pairs (gemm_pair_tcgen05_kernel)
 int g_ffn_mode = 1;         // key 14: 0 = two GEMM launches, 1 = fused feed-forward kernel on CTA pairs
@@ -363,6 +365,7 @@ int vfp_set_tuning(int key, long long value) {
   if (key == 6 && value >= 0 && value <= 4096) { g_topk_prefetch = (int)value; return 0; }
   if (key == 3 && value >= 64 && value <= kConvPassFrames) { g_conv_pass_frames = value; return 0; }
   if (key == 16 && value >= 0 && value <= 1) { g_conv3_ts = (int)value; return 0; }
+  if (key == 17 && value >= 0 && value <= 1) { g_attention_tc = (int)value; return 0; }
   if (key == 15 && value >= 0 && value <= 3) { g_pair_gemm = (int)value; return 0; }
   if (key == 14 && value >= 0 && value <= 1) { g_ffn_mode = (int)value; return 0; }
   if (key == 13 && value >= 0 && value <= 3) { g_conv_mcast = (int)value; return 0; }
@@ -875,6 +878,12 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   // ---- attention blocks ----
   const unsigned ln_grid = (unsigned)((F * 32 + 255) / 256);
   VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_fa_kernel), kAttSmemBytes));
+  AttnTcParams atc{};
+  if (g_attention_tc) {
+    if (make_tmap_rows_bf16(&atc.tmap_qkv, qkv, (uint64_t)F, 3 * kDim, 3 * kDim, 64, 64)) return fail("tensor map encode failed (attention)");
+    atc.items = att_items; atc.out = att; atc.n_units = (int)n_items * 4;
+    VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(attention_tc_kernel), kAtcSmemBytes));
+  }
   // residual updates travel as bf16 `delta` and are folded into the fp32 stream by the next LayerNorm (see there)
   for (int b = 0; b < w->n_attn; ++b) {
     const AttnBlockWeights& a = w->attn[b];
@@ -882,7 +891,12 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     g_prof.mark(kStLayerNorm, st);
     if (token_gemm_bf16(xn, F, kDim, a.tm_qkv, 3 * kDim, a.bqkv, 0, qkv, &a.tm_qkv_h)) return 1;
     g_prof.mark(kStQkv, st);
-    VFP_CUDA(launch_kernel(attention_fa_kernel, dim3((unsigned)n_items), dim3(kAttThreads), kAttSmemBytes, st, qkv, att_items, att, (int)F));
+    if (g_attention_tc) {
+      const int grid = std::min(atc.n_units, 2 * persistent_grid());
+      VFP_CUDA(launch_kernel(attention_tc_kernel, dim3((unsigned)grid), dim3(kAtcThreads), kAtcSmemBytes, st, atc));
+    } else {
+      VFP_CUDA(launch_kernel(attention_fa_kernel, dim3((unsigned)n_items), dim3(kAttThreads), kAttSmemBytes, st, qkv, att_items, att, (int)F));
+    }
     g_prof.mark(kStAttention, st);
     if (token_gemm_bf16(att, F, kDim, a.tm_o, kDim, a.bo, 0, delta, &a.tm_o_h)) return 1;
     g_prof.mark(kStOutProj, st);
