@@ -138,6 +138,31 @@ def test_pipelined_passes_and_host_upload_are_invisible():
         assert cosine(two[c], want[0]) >= COS_BAR
 
 
+def test_attention_key_block_boundaries():
+    """Clip lengths on both sides of the attention kernel's 64-token query / key blocks (one block, exactly two, a one-token
+    tail, several blocks with a masked tail). Each clip must reach the bar against the oracle, must not depend on its
+    neighbours in the packed batch, and the tcgen05 kernel (default) must agree with the mma.sync kernel
+    (vfp_set_tuning(17, 0)) to the rounding of their different P / summation orders."""
+    lib = _native.load()
+    sd = make_state_dict(2, "stress")
+    m = model_for(2, "stress")
+    lengths = [10, 63, 64, 65, 127, 128, 129, 191, 192, 193, 300, 11]
+    clips = make_clips(71, lengths, "colour")
+    want = torch.stack(fingerprint_clips(sd, clips))
+    got = m.fingerprint_clips(clips).cpu()
+    assert lib.vfp_device_error_word() == 0
+    assert cosine(got, want).min() >= COS_BAR
+    rev = m.fingerprint_clips(clips[::-1]).cpu().flip(0)              # other neighbours, other work-item order
+    assert torch.allclose(got, rev, atol=1e-6)
+    try:
+        lib.vfp_set_tuning(17, 0)
+        legacy = m.fingerprint_clips(clips).cpu()
+    finally:
+        lib.vfp_set_tuning(17, 1)
+    assert cosine(legacy, want).min() >= COS_BAR
+    assert cosine(got, legacy).min() > 0.99999
+
+
 def test_clip_longer_than_1024_frames():
     """The positional table of the checkpoint (10 000 rows, model.py:77) is the only length limit."""
     sd = make_state_dict(2, "stress")
