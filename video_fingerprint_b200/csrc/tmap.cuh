@@ -50,6 +50,20 @@ inline int make_tmap_rows_bf16(CUtensorMap* out, const void* base, uint64_t rows
   return r == CUDA_SUCCESS ? 0 : 2;
 }
 
+// fp32 matrix [rows][cols] (dense), box = box_rows x all `cols` columns (cols <= 256), no swizzle.
+inline int make_tmap_rows_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+  if (!enc) return 1;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 4};
+  cuuint32_t box[2] = {(cuuint32_t)cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
 // Row-major output matrix [rows][cols] written by the epilogue in 32-column x 32-row boxes (see EpiBiasActTma).
 inline int make_tmap_out(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, bool bf16) {
   PFN_tensorMapEncodeTiled enc = tensor_map_encoder();

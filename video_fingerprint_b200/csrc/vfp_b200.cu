@@ -870,9 +870,17 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   }
   // ---- multi-scale temporal convolutions (residual) ----
   {
-    const unsigned grid = (unsigned)((F + 4 * kTcTok - 1) / (4 * kTcTok));
-    VFP_CUDA(launch_kernel(temporal_conv_kernel, dim3(grid), dim3(256), 0, st, xa, tok_pos, tok_len, w->tc_w[0], w->tc_b[0], xb, (int)F));
-    VFP_CUDA(launch_kernel(temporal_conv_kernel, dim3(grid), dim3(256), 0, st, xb, tok_pos, tok_len, w->tc_w[1], w->tc_b[1], xa, (int)F));
+    // input rows staged by TMA, persistent CTAs (token_kernels.cuh)
+    VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(temporal_conv_tma_kernel), kTc2SmemBytes));
+    float* bufs[3] = {xa, xb, xa};
+    for (int blk = 0; blk < 2; ++blk) {
+      TemporalConvParams tp{};
+      if (make_tmap_rows_f32(&tp.tmap_x, bufs[blk], (uint64_t)F, kDim, kTc2Rows)) return fail("tensor map encode failed (temporal conv)");
+      tp.tok_pos = tok_pos; tp.tok_len = tok_len; tp.w = w->tc_w[blk]; tp.bias = w->tc_b[blk]; tp.y = bufs[blk + 1];
+      tp.n_tokens = (int)F; tp.n_tiles = (int)((F + kTc2Tok - 1) / kTc2Tok);
+      const int grid = std::min(tp.n_tiles, 2 * persistent_grid());
+      VFP_CUDA(launch_kernel(temporal_conv_tma_kernel, dim3((unsigned)grid), dim3(kTc2Threads), kTc2SmemBytes, st, tp));
+    }
     g_prof.mark(kStTemporalConv, st);
   }
   // ---- attention blocks ----
