@@ -150,9 +150,10 @@ struct TemporalConvParams {
   int n_tiles;
 };
 
-// 8 tokens x 4 branches of one group. Interior tokens: one FFMA per multiply-add. kMasked (a token within 5 of an end of its
-// clip is among the 8): the tap's dot product is formed first and enters the accumulator through an FFMA with factor 1.0 or
-// 0.0, so the masked path has no branches either (rows of a neighbouring clip are finite, TMA fill is zero).
+// 8 tokens x 4 branches of one group, one FFMA per multiply-add. kMasked (a token within 5 of an end of its clip is among the
+// 8): the input values of a tap outside the clip are ANDed to zero, so the masked path has no branches and gives a token
+// with all taps valid exactly the bits the unmasked path gives it - a token's result must not depend on which tokens it
+// shares its slice with (weights are finite, so fma(w, 0, acc) = acc).
 template <bool kMasked>
 __device__ __forceinline__ void temporal_conv_oct(const float* __restrict__ xt /*tile row of the first token's tap 0*/, const float4 (*ws)[64], int g,
                                                   const unsigned (&mask)[8], float (&acc)[8][4]) {
@@ -169,19 +170,18 @@ __device__ __forceinline__ void temporal_conv_oct(const float* __restrict__ xt /
     if (tap >= 4 && tap <= 6) w0 = ws[tap - 4][g];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const float4 xi = rows[(tap + q) & 7];
-      if (kMasked) {
-        const float f = ((mask[q] >> tap) & 1u) ? 1.0f : 0.0f;
-        acc[q][3] = fmaf(f, w3.x * xi.x + w3.y * xi.y + w3.z * xi.z + w3.w * xi.w, acc[q][3]);
-        if (tap >= 2 && tap <= 8) acc[q][2] = fmaf(f, w2.x * xi.x + w2.y * xi.y + w2.z * xi.z + w2.w * xi.w, acc[q][2]);
-        if (tap >= 3 && tap <= 7) acc[q][1] = fmaf(f, w1.x * xi.x + w1.y * xi.y + w1.z * xi.z + w1.w * xi.w, acc[q][1]);
-        if (tap >= 4 && tap <= 6) acc[q][0] = fmaf(f, w0.x * xi.x + w0.y * xi.y + w0.z * xi.z + w0.w * xi.w, acc[q][0]);
-      } else {
-        acc[q][3] = fmaf(w3.w, xi.w, fmaf(w3.z, xi.z, fmaf(w3.y, xi.y, fmaf(w3.x, xi.x, acc[q][3]))));
-        if (tap >= 2 && tap <= 8) acc[q][2] = fmaf(w2.w, xi.w, fmaf(w2.z, xi.z, fmaf(w2.y, xi.y, fmaf(w2.x, xi.x, acc[q][2]))));
-        if (tap >= 3 && tap <= 7) acc[q][1] = fmaf(w1.w, xi.w, fmaf(w1.z, xi.z, fmaf(w1.y, xi.y, fmaf(w1.x, xi.x, acc[q][1]))));
-        if (tap >= 4 && tap <= 6) acc[q][0] = fmaf(w0.w, xi.w, fmaf(w0.z, xi.z, fmaf(w0.y, xi.y, fmaf(w0.x, xi.x, acc[q][0]))));
+      float4 xi = rows[(tap + q) & 7];
+      if (kMasked) {   // a tap outside the clip contributes fma(w, 0, acc) = acc: the arithmetic of the valid taps is the same in both paths
+        const uint32_t keep = 0u - ((mask[q] >> tap) & 1u);
+        xi.x = __uint_as_float(__float_as_uint(xi.x) & keep);
+        xi.y = __uint_as_float(__float_as_uint(xi.y) & keep);
+        xi.z = __uint_as_float(__float_as_uint(xi.z) & keep);
+        xi.w = __uint_as_float(__float_as_uint(xi.w) & keep);
       }
+      acc[q][3] = fmaf(w3.w, xi.w, fmaf(w3.z, xi.z, fmaf(w3.y, xi.y, fmaf(w3.x, xi.x, acc[q][3]))));
+      if (tap >= 2 && tap <= 8) acc[q][2] = fmaf(w2.w, xi.w, fmaf(w2.z, xi.z, fmaf(w2.y, xi.y, fmaf(w2.x, xi.x, acc[q][2]))));
+      if (tap >= 3 && tap <= 7) acc[q][1] = fmaf(w1.w, xi.w, fmaf(w1.z, xi.z, fmaf(w1.y, xi.y, fmaf(w1.x, xi.x, acc[q][1]))));
+      if (tap >= 4 && tap <= 6) acc[q][0] = fmaf(w0.w, xi.w, fmaf(w0.z, xi.z, fmaf(w0.y, xi.y, fmaf(w0.x, xi.x, acc[q][0]))));
     }
   }
 }
