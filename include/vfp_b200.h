@@ -170,7 +170,8 @@ int vfp_profile_read(double* stage_ms, int n_stages, uint64_t* launches, int res
  * separate streams (1); key 10: join kernel, 0 = one CTA per tile, 1 = A-resident, 2 = A-resident CTA pairs (2); key 11:
  * self joins compute the upper triangle and mirror the pairs (1); key 12: join panel width in column tiles (512); key 13:
  * TMA multicast of the conv3 / conv4 filter tile across a CTA pair, bit mask (0); key 14: 1 = both MLP linears in one kernel (1);
- * key 15: CTA-pair GEMM, bit 0 conv4, bit 1 QKV / out-projection (1); key 16: conv3 with its filters in tensor memory (1).
+ * key 15: CTA-pair GEMM, bit 0 conv4, bit 1 QKV / out-projection (1); key 16: conv3 with its filters in tensor memory (1);
+ * key 17: attention on tcgen05 (1) or the mma.sync twin kept for cross-checks (0).
  * Every setting produces the same results up to fp32 summation order (scripts/dev_tuning_parity.py). */
 int vfp_set_tuning(int key, long long value);
 
