@@ -126,8 +126,9 @@ int vfp3d_forward(const vfp3d_weights* w, const void* frames, int frame_dtype, i
  * INTER_AREA) so that the short side becomes 64 (new size truncated with int() like the reference), then the centre
  * 64 x 64 crop. `frames_hwc`: device uint8 (n_frames, height, width, 3), all frames of one size; `out_hwc64`: device
  * uint8 (n_frames, 64, 64, 3), which vfp_forward accepts as VFP_FRAME_U8_HWC (the /255 and the HWC->CHW permute of
- * fingerprint.py:210-212 happen inside the stem kernel). Bit-exact with OpenCV 4.x INTER_AREA down-scaling (general,
- * integer-factor and 2 x 2 code paths); frames with a side below 64 pixels (up-scaling) are rejected. */
+ * fingerprint.py:210-212 happen inside the stem kernel). Bit-exact with OpenCV 4.x INTER_AREA: down-scaling (general,
+ * integer-factor and 2 x 2 code paths) and, for frames with a side below 64 pixels, the up-scaling branch (8-bit fixed-point
+ * bilinear kernels with the area coefficient rule). */
 size_t vfp_preprocess_workspace_bytes(int height, int width);
 int vfp_preprocess_frames(const uint8_t* frames_hwc, int n_frames, int height, int width, uint8_t* out_hwc64,
                           void* workspace, size_t workspace_bytes, void* stream);

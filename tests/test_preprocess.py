@@ -1,5 +1,6 @@
 """Frame preprocessing (/root/reference/fingerprint.py:186-214): INTER_AREA resize to a short
-side of 64 + centre crop. Integer / byte work -> bit-exact everywhere.
+side of 64 + centre crop (down-scaling and, for frames with a side below 64 px, up-scaling). Integer / byte work -> bit-exact
+everywhere.
 
 CPU: the NumPy oracle against tests/golden/preprocess.npz (what the reference's unmodified ``_preprocess_frames`` returned
 here, i.e. cv2 4.13) and, where cv2 is importable, live against cv2 on random sizes. GPU (-m gpu): vfp_preprocess_frames
@@ -30,7 +31,7 @@ def test_oracle_matches_reference_golden(case):
 def test_oracle_matches_live_cv2():
     cv2 = pytest.importorskip("cv2")
     rng = np.random.default_rng(5)
-    for h, w in [(97, 143), (150, 100), (128, 256), (64, 90), (256, 256), (199, 64)]:
+    for h, w in [(97, 143), (150, 100), (128, 256), (64, 90), (256, 256), (199, 64), (48, 50), (63, 64), (17, 9), (1, 1), (3, 200), (40, 40)]:
         frame = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         nh, nw = po.target_size(h, w)
         assert np.array_equal(po.resize_area(frame, nw, nh), cv2.resize(frame, (nw, nh), interpolation=cv2.INTER_AREA)), (h, w)
@@ -56,15 +57,16 @@ def test_device_preprocess_is_bit_exact(case):
 @pytest.mark.gpu
 def test_device_preprocess_inputs_errors_and_forward():
     import video_fingerprint_b200 as vfp
-    from video_fingerprint_b200 import _native
 
     frames = po.make_frames("odd", 12, 150, 231)
     want = po.preprocess_frames(frames[:2])
     a = vfp.preprocess_frames_device(list(frames))                     # list of arrays
     b = vfp.preprocess_frames_device(torch.from_numpy(frames).cuda())  # device tensor
     assert torch.equal(a, b) and np.array_equal(a[:2].cpu().numpy(), want)
-    with pytest.raises(_native.NativeError):
-        vfp.preprocess_frames_device(np.zeros((1, 48, 100, 3), np.uint8))   # would up-scale
+    rng = np.random.default_rng(3)
+    for h, w in [(48, 100), (5, 9), (63, 63), (1, 1), (30, 500)]:                # a side below 64 px: INTER_AREA up-scales
+        tiny = rng.integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+        assert np.array_equal(vfp.preprocess_frames_device(tiny).cpu().numpy(), po.preprocess_frames(tiny)), (h, w)
     with pytest.raises(ValueError):
         vfp.preprocess_frames_device(np.zeros((1, 100, 100, 3), np.float32))
     # decoded frames -> embedding, against the float clip the reference would build from the same preprocessing

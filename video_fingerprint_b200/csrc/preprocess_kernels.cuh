@@ -1,7 +1,7 @@
 // On-device restatement of the scanner's frame preprocessing (/root/reference/fingerprint.py:186-214 _preprocess_frames):
 // cv2.resize(frame, (new_w, new_h), INTER_AREA) so that the short side becomes 64, centre crop to 64 x 64. The uint8 result
 // (decoder layout H, W, 3) feeds the fused stem directly (frame_dtype VFP_FRAME_U8_HWC, which also does the /255).
-// Bit-exact with OpenCV 4.x for down-scaling (both scale factors >= 1), its three code paths:
+// Bit-exact with OpenCV 4.x. Down-scaling (both scale factors >= 1) has three code paths (up-scaling: see the end of the file):
 //   * general (non-integer scale): float tables of (source index, weight) per destination index (computeResizeAreaTab);
 //     per source row   buf = buf + S * alpha   over the x entries in order, then   sum = beta * buf   (first row) or
 //     sum = sum + beta * buf; saturate_cast<uchar> = round half to even. Separate fmul / fadd, exactly OpenCV's order.
@@ -83,6 +83,35 @@ __global__ void __launch_bounds__(192) preprocess_area_kernel(const PreprocessPa
   else v = (float)((isum + 2) >> 2);
   const int r = __float2int_rn(v);    // round half to even, like cvRound
   p.dst[(((size_t)f * 64 + dy) * 64 + dx) * 3 + c] = (uint8_t)min(max(r, 0), 255);
+}
+
+
+// Up-scaling (a frame side below 64 px): cv::resize leaves the area code and runs its 8-bit bilinear kernels with the
+// INTER_AREA coefficient rule (imgproc/src/resize.cpp: HResizeLinear<uchar, int, short, 2048> and VResizeLinear<uchar, int,
+// short, FixedPtCast<int, uchar, 22>>): horizontal pass in int32 with two 11-bit coefficients, vertical pass
+// (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2. The tables of the 64 x 64 crop window travel in the kernel
+// parameters; such frames are tiny, so every thread reads its four source bytes straight from global memory.
+struct PreprocessUpParams {
+  const uint8_t* src;    // [frames][H][W][3]
+  uint8_t* dst;          // [frames][64][64][3]
+  int H, W;
+  int xo[64], yo[64];            // source column / row of the first sample
+  short xa[64][2], yb[64][2];    // 11-bit fixed-point coefficient pairs
+};
+
+__global__ void __launch_bounds__(192) preprocess_linear_kernel(const __grid_constant__ PreprocessUpParams p) {
+  const int dy = blockIdx.x, f = blockIdx.y;
+  const int dx = threadIdx.x / 3, c = threadIdx.x - 3 * dx;
+  const uint8_t* frame = p.src + (size_t)f * p.H * p.W * 3;
+  const int s0 = p.xo[dx], s1 = min(s0 + 1, p.W - 1);
+  const int r0 = p.yo[dy], r1 = min(r0 + 1, p.H - 1);
+  const int a0 = p.xa[dx][0], a1 = p.xa[dx][1], b0 = p.yb[dy][0], b1 = p.yb[dy][1];
+  const uint8_t* row0 = frame + (size_t)r0 * p.W * 3;
+  const uint8_t* row1 = frame + (size_t)r1 * p.W * 3;
+  const int h0 = row0[s0 * 3 + c] * a0 + row0[s1 * 3 + c] * a1;
+  const int h1 = row1[s0 * 3 + c] * a0 + row1[s1 * 3 + c] * a1;
+  const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+  p.dst[(((size_t)f * 64 + dy) * 64 + dx) * 3 + c] = (uint8_t)v;
 }
 
 }  // namespace vfp

@@ -1217,6 +1217,21 @@ void area_table(int ssize, int dsize, double scale, int d0, std::vector<int>* be
   }
   (*begin)[64] = (int)si->size();
 }
+// cv::resize's coefficient loop with area_mode = true, ksize = 2, 8-bit fixed point (imgproc/src/resize.cpp), destination
+// indices [d0, d0 + 64): sx = cvFloor(dx * scale), fx = (float)((dx + 1) - (sx + 1) * inv_scale) reduced to [0, 1); at the last
+// source sample the pair degenerates to (2048, 0); coefficients = saturate_cast<short>(c * 2048) (round half to even)
+void linear_area_table(int ssize, int dsize, int d0, int* ofs, short (*coef)[2]) {
+  const double inv_scale = (double)dsize / ssize, scale = 1.0 / inv_scale;
+  for (int d = d0; d < d0 + 64; ++d) {
+    int s = (int)floor(d * scale);
+    float f = (float)((d + 1) - (s + 1) * inv_scale);
+    f = f <= 0 ? 0.0f : f - floorf(f);
+    if (s >= ssize - 1) { f = 0.0f; s = ssize - 1; }
+    ofs[d - d0] = s;
+    coef[d - d0][0] = (short)lrintf((1.0f - f) * 2048.0f);
+    coef[d - d0][1] = (short)lrintf(f * 2048.0f);
+  }
+}
 }  // namespace
 
 size_t vfp_preprocess_workspace_bytes(int height, int width) {
@@ -1229,12 +1244,21 @@ int vfp_preprocess_frames(const uint8_t* frames_hwc, int n_frames, int height, i
                           size_t workspace_bytes, void* stream) {
   if (!frames_hwc || !out_hwc64 || !workspace) return fail("vfp_preprocess_frames: null argument");
   if (n_frames <= 0 || n_frames > 65535) return fail("vfp_preprocess_frames: 1 .. 65535 frames per call");
-  if (height < 64 || width < 64) return fail("vfp_preprocess_frames: frames smaller than 64 pixels are not supported (INTER_AREA would up-scale)");
+  if (height < 1 || width < 1) return fail("vfp_preprocess_frames: empty frames");
   if (workspace_bytes < vfp_preprocess_workspace_bytes(height, width)) return fail("vfp_preprocess_frames: workspace too small");
   // fingerprint.py:190-196
   int new_w, new_h;
   if (height < width) { new_h = 64; new_w = (int)((double)width * 64 / height); }
   else { new_w = 64; new_h = (int)((double)height * 64 / width); }
+  if (height < 64 || width < 64) {   // a side below 64 px: both axes are up-scaled (preprocess_kernels.cuh, end of file)
+    PreprocessUpParams up{};
+    up.src = frames_hwc; up.dst = out_hwc64; up.H = height; up.W = width;
+    linear_area_table(width, new_w, (new_w - 64) / 2, up.xo, up.xa);
+    linear_area_table(height, new_h, (new_h - 64) / 2, up.yo, up.yb);
+    preprocess_linear_kernel<<<dim3(64, (unsigned)n_frames), 192, 0, static_cast<cudaStream_t>(stream)>>>(up);
+    VFP_CUDA(cudaGetLastError());
+    return 0;
+  }
   // cv::resize: inv_scale = dsize / ssize, scale = 1. / inv_scale (not ssize / dsize: the last bit can differ)
   const double scale_x = 1.0 / ((double)new_w / width), scale_y = 1.0 / ((double)new_h / height);
   const int start_h = (new_h - 64) / 2, start_w = (new_w - 64) / 2;   // fingerprint.py:201-202
