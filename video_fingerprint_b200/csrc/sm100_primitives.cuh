@@ -209,8 +209,14 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// Default semantics (.release at CTA scope), as CUTLASS's ClusterBarrier::arrive(cta_id) uses for consumer -> leader signals.
+// What the leader's issuer must be able to rely on was ordered before the arrive by the caller: tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync for accumulators that were read, fence.proxy.async for shared-memory operands that were
+// written (both act inside the arriving CTA, which is where the tensor core will read them). Spelling the arrive
+// .release.cluster makes ptxas emit MEMBAR.ALL.GPU / MEMBAR.SC.SYS + ERRBAR in front of it: ncu attributed 24 % of all warp
+// samples of the fused MLP kernel to that stall.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // local destination, completion bytes counted on the mbarrier at shared::cluster address `bar_cluster_addr` (the leader's)
 __device__ __forceinline__ void tma_load_2d_2cta(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1) {
