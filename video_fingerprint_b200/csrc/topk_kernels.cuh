@@ -325,9 +325,18 @@ inline TopKWs topk_ws_layout(int64_t n_q, int64_t n_db) {
   };
   const int64_t m_tiles = (n_q + 127) / 128;
   const int64_t n_tiles = (n_db + 255) / 256;
-  // enough work items to fill the GPU a few times over, without splitting more than necessary
+  // Database segments per query tile: work item = (128 query rows, one contiguous segment). More segments fill the last round
+  // of the persistent grid better, but every (row, segment) heap starts cold: its first ~64 ln(rows / 64) candidates are
+  // all insertions. Measured on 10 M rows (profiles/r02_bench_n*.json, cfg 5): an item costs 7.7 ns per database row plus
+  // ~1 ms per e-fold of segment length; e.g. 12 500 queries per GPU: 8 segments 125 ms, 3 segments (two full rounds) 74 ms.
   int seg = 1;
-  while (seg < kTopKMaxSegments && m_tiles * seg < 4 * 148 && seg * 2 <= n_tiles) seg *= 2;
+  double best = 1e300;
+  for (int cand = 1; cand <= kTopKMaxSegments && cand <= n_tiles; ++cand) {
+    const double len = (double)n_db / cand;
+    const double item_ms = 7.68e-6 * len + 1.0 * log(std::max(len / 64.0, 2.0));
+    const double cost = ceil((double)m_tiles * cand / 148.0) * item_ms;
+    if (cost < 0.97 * best) { best = cost; seg = cand; }
+  }
   L.n_segments = seg;
   L.rows_padded = m_tiles * 128;
   const int64_t batch = std::min<int64_t>(n_q, kTopKBatch);
