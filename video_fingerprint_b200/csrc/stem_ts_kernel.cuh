@@ -49,6 +49,10 @@ constexpr int kTsColAcc = 0, kTsColA = 256, kTsColD = 384;  // TMEM column map: 
 // development knock-out mask (compile time, -DVFP_STEM_KNOCKOUT=mask): 1 no output store, 2 no transposition, 4 no frame
 // copies, 8 no conv2 UMMAs, 16 no conv1 UMMAs, 32 no conv1-epilogue stores, 64 no generator loads, 128 no conv2-epilogue
 // work, 256 no conv1-epilogue TMEM loads, 512 no generator TMEM stores (1023 = the bare barrier skeleton)
+// development experiment (-DVFP_STEM_HALFB=1, wrong results): every UMMA of the stem reads half of its weight operand, which is what a CTA pair would read
+#ifndef VFP_STEM_HALFB
+#define VFP_STEM_HALFB 0
+#endif
 #ifndef VFP_STEM_KNOCKOUT
 #define VFP_STEM_KNOCKOUT 0
 #endif
@@ -261,7 +265,7 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
     } else if (warp == 1) {
       // ------------------------------ conv1 UMMA issuer (TS mode) ------------------------------
       // the whole warp waits (a converged try_wait wakes up faster than a single-lane one), lane 0 issues
-      constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
+      constexpr uint32_t idesc64 = umma_idesc_bf16(128, VFP_STEM_HALFB ? 32 : 64);
       mbar_wait_relaxed(w_full, 0);
       const uint32_t w1_lo = desc_lo_sw128(smem_u32(w1buf));
       int ab = 0;
@@ -287,8 +291,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_ts_kernel(const __grid_c
       }
     } else if (warp == 3) {
       // ------------------------------ conv2 UMMA issuer ------------------------------
-      constexpr uint32_t idesc64 = umma_idesc_bf16(128, 64);
-      constexpr uint32_t idesc128 = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc64 = umma_idesc_bf16(128, VFP_STEM_HALFB ? 32 : 64);
+      constexpr uint32_t idesc128 = umma_idesc_bf16(128, VFP_STEM_HALFB ? 64 : 128);
       mbar_wait_relaxed(w_full, 0);
       const uint32_t w2_lo = desc_lo_sw128(smem_u32(w2buf));
       const uint32_t c1_lo = desc_lo_sw128(smem_u32(c1buf));
