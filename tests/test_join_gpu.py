@@ -164,3 +164,23 @@ def test_join_splits_query_rows_when_candidates_exceed_the_buffer(monkeypatch):
     got = fp.threshold_join(E, 0.9)
     assert_pairs_match(got, want, 0.9, band=1e-5)
     assert np.all(np.diff(got[0]) >= 0)
+
+
+def test_duplicate_pairs_give_the_same_groups_as_the_full_pair_list():
+    """find_duplicates' direct path only ships the rows with at least two hits to the host, ordered on the device; the greedy
+    grouping must come out as on the complete (i, j)-sorted pair list (and as the oracle's)."""
+    rng = np.random.default_rng(17)
+    n = 5000
+    E = rng.standard_normal((n, 256)).astype(np.float32)
+    E /= np.linalg.norm(E, axis=1, keepdims=True)
+    for a, b in [(3, 700), (3, 701), (700, 900), (50, 51), (1200, 4999), (4000, 4001), (4001, 4002)]:
+        v = E[a] + 0.02 * rng.standard_normal(256).astype(np.float32)
+        E[b] = v / np.linalg.norm(v)
+    E[2500:2520] = E[10]                                   # a block of exact copies
+    full = vfp.group_pairs_direct(n, *vfp.threshold_join(E, 0.95))
+    pi, pj, ps = vfp.duplicate_pairs(E, 0.95)
+    assert len(pi) < 600 and np.all(np.diff(pi * n + pj) > 0)          # few rows survive; strictly (i, j)-ordered
+    lean = vfp.group_pairs_direct(n, pi, pj, ps)
+    assert [[i for i, _ in g] for g in lean] == [[i for i, _ in g] for g in full] and len(full) >= 5
+    want = join_oracle.group_direct(n, *join_oracle.threshold_pairs(E, 0.95))
+    assert [[i for i, _ in g] for g in lean] == [[i for i, _ in g] for g in want]

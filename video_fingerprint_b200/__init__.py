@@ -13,6 +13,7 @@ All device work goes through libvfp_b200.so (include/vfp_b200.h); there is no CP
 from .model import VideoFingerprint3D, VideoFingerprintAttention, create_model  # noqa: F401
 from .fingerprint import (  # noqa: F401
     VideoFingerprintScanner,
+    duplicate_pairs,
     group_pairs_direct,
     group_pairs_topk,
     preprocess_frames_device,
@@ -35,6 +36,6 @@ __all__ = [
     "threshold_join_device",
     "topk_inner_product",
     "topk_inner_product_device",
-    "group_pairs_direct",
+    "duplicate_pairs", "group_pairs_direct",
     "group_pairs_topk",
 ]
