@@ -282,10 +282,12 @@ __global__ void __launch_bounds__(kTc2Threads, 2) temporal_conv_tma_kernel(const
 
 // ---------------------------------------------------------------------------------------------
 // Multi-head self-attention (model.py:143) over PACKED clips, flash-style on the register-fragment tensor path
-// (mma.sync m16n8k16 bf16 -> fp32). head_dim is 32, so QK^T and PV of one head are 128 x 128 x 32 problems: a 128-row UMMA
-// tile would spend its time in TMEM round trips and mbarrier hand-offs (a chain of ~2 600 cycles per head and key block,
-// estimated from the hand-off costs measured in profiles/r01_microbench_handoff.txt), while eight warps with the scores in
-// registers need ~4 000 HMMA cycles per 128 tokens for all eight heads - and the whole stage is 0.7 % of the forward's FLOPs.
+// (mma.sync m16n8k16 bf16 -> fp32). NOT the production kernel any more: attention_tc_kernel.cuh (tcgen05, scores / P / PV in
+// tensor memory) is 1.7x faster and is what vfp_forward launches; this one stays as an independently written twin that the
+// boundary test compares it with (vfp_set_tuning(17, 0), tests/test_forward_gpu.py::test_attention_key_block_boundaries).
+// (The estimate that kept attention off tcgen05 for a round - a serial chain of ~2 600 cycles of TMEM round trips and
+// mbarrier hand-offs per head and key block - was right about the chain and wrong about the conclusion: two CTAs per SM and
+// softmax threads that run one step ahead of the PV products hide it.)
 //
 // A CTA owns one ITEM = 64 consecutive query tokens of ONE clip (the host lists the items: ceil(T / 64) per clip) and walks that
 // clip's keys in blocks of 64 tokens from the clip's first token, so what a clip gets never depends on what it is packed next
