@@ -42,6 +42,29 @@ __device__ __forceinline__ uint32_t gelu_erf2_f16(float2 x) {
       : "r"(xh), "r"(0x28912891u) /* 0.0356774 */, "r"(0x3A623A62u) /* 0.7978846 */, "r"(0x38003800u) /* 0.5 */);
   return y;
 }
+// accumulator pair + bias pair (already f16x2) -> GELU -> bf16x2: the bias joins after the conversion to f16x2 (the packed fp32
+// add it replaces, FADD2, costs about four times an HADD2 in issue slots: ncu source page of the fused MLP kernel)
+__device__ __forceinline__ uint32_t gelu_bias_bf16x2(float2 acc, uint32_t bias_h2) {
+  uint32_t xh, y;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(xh) : "f"(acc.y), "f"(acc.x));
+  asm("{\n\t"
+      ".reg .b32 x, x2, p, u, t, hx;\n\t"
+      "add.rn.f16x2 x, %1, %5;\n\t"
+      "mul.rn.f16x2 x2, x, x;\n\t"
+      "fma.rn.f16x2 p, x2, %2, %3;\n\t"
+      "mul.rn.f16x2 u, x, p;\n\t"
+      "tanh.approx.f16x2 t, u;\n\t"
+      "mul.rn.f16x2 hx, x, %4;\n\t"
+      "fma.rn.f16x2 %0, hx, t, hx;\n\t"
+      "}"
+      : "=r"(y)
+      : "r"(xh), "r"(0x28912891u) /* 0.0356774 */, "r"(0x3A623A62u) /* 0.7978846 */, "r"(0x38003800u) /* 0.5 */, "r"(bias_h2));
+  float lo, hi;
+  asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(y));
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // fp32 pair in, fp32 pair out (callers that keep working in fp32)
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const uint32_t y = gelu_erf2_f16(x);

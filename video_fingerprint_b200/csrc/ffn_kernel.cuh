@@ -126,7 +126,13 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_pair_kernel(const __grid_c
     tmem_alloc_2cta(tmem_slot, 512);
     tmem_relinquish_2cta();
   }
-  for (int i = threadIdx.x; i < kFfnHidden + 256; i += kFfnThreads) sbias[i] = i < kFfnHidden ? __ldg(p.b1 + i) : __ldg(p.b2 + i - kFfnHidden);
+  // b1 as f16x2 pairs (the activation adds it after converting the accumulator to f16x2), b2 as fp32
+  uint32_t* sbias_h = reinterpret_cast<uint32_t*>(sbias);
+  for (int i = threadIdx.x; i < kFfnHidden / 2; i += kFfnThreads) {
+    const __half2 h = __floats2half2_rn(__ldg(p.b1 + 2 * i), __ldg(p.b1 + 2 * i + 1));
+    sbias_h[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  for (int i = threadIdx.x; i < 256; i += kFfnThreads) sbias[kFfnHidden + i] = __ldg(p.b2 + i);
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();
@@ -310,14 +316,14 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_pair_kernel(const __grid_c
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           uint32_t(&v)[32] = cc ? vb : va;
-          const float* bias = sbias + c * kFfnChunk + cq * 64 + cc * 32;
+          const uint32_t* bias = sbias_h + (c * kFfnChunk + cq * 64 + cc * 32) / 2;
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(bias + i);
-            const float2 y0 = gelu_erf2(fadd2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), make_float2(bb.x, bb.y)));
-            const float2 y1 = gelu_erf2(fadd2(make_float2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), make_float2(bb.z, bb.w)));
-            packed[cc * 16 + i / 2] = pack_bf16x2(y0.x, y0.y);
-            packed[cc * 16 + i / 2 + 1] = pack_bf16x2(y1.x, y1.y);
+          for (int i = 0; i < 32; i += 8) {
+            const uint4 bb = *reinterpret_cast<const uint4*>(bias + i / 2);
+            packed[cc * 16 + i / 2] = gelu_bias_bf16x2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), bb.x);
+            packed[cc * 16 + i / 2 + 1] = gelu_bias_bf16x2(make_float2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3])), bb.y);
+            packed[cc * 16 + i / 2 + 2] = gelu_bias_bf16x2(make_float2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5])), bb.z);
+            packed[cc * 16 + i / 2 + 3] = gelu_bias_bf16x2(make_float2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7])), bb.w);
           }
         }
       }
