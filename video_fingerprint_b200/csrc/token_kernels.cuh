@@ -33,16 +33,19 @@ __global__ void token_map_kernel(const int* __restrict__ cu, int n_clips, int n_
 }
 
 // ---------------------------------------------------------------------------------------------
-// (x += delta) ; y = LayerNorm(x) over 256 channels. fp32 residual stream in/out, bf16 normalised copy out.
-// The residual GEMMs (attention out-projection, MLP down-projection) emit their result as a bf16 `delta` through
-// the TMA store path; the add into the fp32 stream happens here, where the row is being read anyway, instead of
-// in the GEMM epilogue (whose row-per-thread layout makes fp32 read-modify-write uncoalesced).
-// One warp per token, 8 channels per lane.
+// v = (x + delta_a) + delta_f ; y = LayerNorm(v) over 256 channels; x = v if write_x. fp32 residual stream, bf16 normalised
+// copy out. The residual GEMMs (attention out-projection, MLP down-projection) emit their result as bf16 deltas through the
+// TMA store path; the add into the fp32 stream happens here, where the row is being read anyway, instead of in the GEMM
+// epilogue (whose row-per-thread layout makes fp32 read-modify-write uncoalesced). The stream is only WRITTEN once per block:
+// a block's second LayerNorm (before the MLP) normalises x + delta_a without storing it, and the next block's first
+// LayerNorm adds both deltas in the same order - the bits of the stream are what two stores per block gave, for 1 KB per
+// token and block less traffic. One warp per token, 8 channels per lane.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 add_layernorm_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta /*nullable*/,
+                          const __nv_bfloat16* __restrict__ delta2 /*nullable, added after delta*/,
                           const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
-                          int n_tokens) {
+                          int n_tokens, int write_x) {
   pdl_launch_dependents();
   pdl_wait();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -60,8 +63,20 @@ add_layernorm_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict
       v[2 * e] += f.x;
       v[2 * e + 1] += f.y;
     }
-    xr[0] = make_float4(v[0], v[1], v[2], v[3]);
-    xr[1] = make_float4(v[4], v[5], v[6], v[7]);
+    if (delta2) {
+      const uint4 d2 = reinterpret_cast<const uint4*>(delta2 + (size_t)warp * kDim)[lane];
+      const __nv_bfloat162* dp2 = reinterpret_cast<const __nv_bfloat162*>(&d2);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(dp2[e]);
+        v[2 * e] += f.x;
+        v[2 * e + 1] += f.y;
+      }
+    }
+    if (write_x) {
+      xr[0] = make_float4(v[0], v[1], v[2], v[3]);
+      xr[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
   }
   float s = 0.f;
 #pragma unroll
@@ -87,10 +102,11 @@ add_layernorm_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict
   reinterpret_cast<uint4*>(y + (size_t)warp * kDim)[lane] = o;
 }
 
-// (x += delta) ; xbf = bf16(x): closes the last attention block and feeds the pooling GEMM. 8 channels per thread.
+// x = (x + delta) + delta2 ; xbf = bf16(x): closes the last attention block and feeds the pooling GEMM. 8 channels per thread.
 __global__ void __launch_bounds__(256)
 add_convert_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ delta /*nullable*/,
-                        __nv_bfloat16* __restrict__ xbf, long long n8) {
+                        const __nv_bfloat16* __restrict__ delta2 /*nullable, added after delta*/, __nv_bfloat16* __restrict__ xbf,
+                        long long n8) {
   pdl_launch_dependents();
   pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -106,6 +122,16 @@ add_convert_bf16_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__
       const float2 f = __bfloat1622float2(dp[e]);
       v[2 * e] += f.x;
       v[2 * e + 1] += f.y;
+    }
+    if (delta2) {
+      const uint4 d2 = reinterpret_cast<const uint4*>(delta2)[i];
+      const __nv_bfloat162* dp2 = reinterpret_cast<const __nv_bfloat162*>(&d2);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(dp2[e]);
+        v[2 * e] += f.x;
+        v[2 * e + 1] += f.y;
+      }
     }
     xr[0] = make_float4(v[0], v[1], v[2], v[3]);
     xr[1] = make_float4(v[4], v[5], v[6], v[7]);

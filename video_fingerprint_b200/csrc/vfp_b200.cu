@@ -268,7 +268,7 @@ int g_join_symmetric = 1;   // key 11: self joins screen the upper triangle only
 int g_join_panel_tiles = 512;  // key 12: database column tiles (of 128 rows) per L2 panel
 
 struct TokenWs {
-  size_t cu, att_items, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, h, logits, xbf, pooled, pooled_bf, head_h, total;
+  size_t cu, att_items, tok_pos, tok_len, feat, xa, xb, xn, qkv, att, delta, delta2, h, logits, xbf, pooled, pooled_bf, head_h, total;
 };
 struct ConvWs {
   size_t c1, c2, c3, total;
@@ -292,6 +292,7 @@ TokenWs token_ws_layout(int64_t F, int64_t C) {
   L.qkv = take((size_t)F * 3 * kDim * 2);
   L.att = take((size_t)F * kDim * 2);
   L.delta = take((size_t)F * kDim * 2);
+  L.delta2 = take((size_t)F * kDim * 2);
   L.h = take((size_t)F * 4 * kDim * 2);
   L.logits = take((size_t)F * kDim * 4);
   L.xbf = take((size_t)F * kDim * 2);
@@ -792,7 +793,8 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   __nv_bfloat16* xn = reinterpret_cast<__nv_bfloat16*>(ws + L.xn);
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws + L.qkv);
   __nv_bfloat16* att = reinterpret_cast<__nv_bfloat16*>(ws + L.att);
-  __nv_bfloat16* delta = reinterpret_cast<__nv_bfloat16*>(ws + L.delta);
+  __nv_bfloat16* delta = reinterpret_cast<__nv_bfloat16*>(ws + L.delta);     // attention out-projection of the current block
+  __nv_bfloat16* delta_f = reinterpret_cast<__nv_bfloat16*>(ws + L.delta2);  // MLP output of the previous block
   __nv_bfloat16* hbuf = reinterpret_cast<__nv_bfloat16*>(ws + L.h);
   float* logits = reinterpret_cast<float*>(ws + L.logits);
   __nv_bfloat16* xbf = reinterpret_cast<__nv_bfloat16*>(ws + L.xbf);
@@ -895,7 +897,7 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
   // residual updates travel as bf16 `delta` and are folded into the fp32 stream by the next LayerNorm (see there)
   for (int b = 0; b < w->n_attn; ++b) {
     const AttnBlockWeights& a = w->attn[b];
-    VFP_CUDA(launch_kernel(add_layernorm_bf16_kernel, dim3(ln_grid), dim3(256), 0, st, xa, b > 0 ? delta : nullptr, a.ln1_w, a.ln1_b, xn, (int)F));
+    VFP_CUDA(launch_kernel(add_layernorm_bf16_kernel, dim3(ln_grid), dim3(256), 0, st, xa, b > 0 ? delta : nullptr, b > 0 ? delta_f : nullptr, a.ln1_w, a.ln1_b, xn, (int)F, 1));
     g_prof.mark(kStLayerNorm, st);
     if (token_gemm_bf16(xn, F, kDim, a.tm_qkv, 3 * kDim, a.bqkv, 0, qkv, &a.tm_qkv_h)) return 1;
     g_prof.mark(kStQkv, st);
@@ -908,18 +910,18 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     g_prof.mark(kStAttention, st);
     if (token_gemm_bf16(att, F, kDim, a.tm_o, kDim, a.bo, 0, delta, &a.tm_o_h)) return 1;
     g_prof.mark(kStOutProj, st);
-    VFP_CUDA(launch_kernel(add_layernorm_bf16_kernel, dim3(ln_grid), dim3(256), 0, st, xa, delta, a.ln2_w, a.ln2_b, xn, (int)F));
+    VFP_CUDA(launch_kernel(add_layernorm_bf16_kernel, dim3(ln_grid), dim3(256), 0, st, xa, delta, (const __nv_bfloat16*)nullptr, a.ln2_w, a.ln2_b, xn, (int)F, 0));
     g_prof.mark(kStLayerNorm, st);
     if (g_ffn_mode == 0) {
       if (token_gemm_bf16(xn, F, kDim, a.tm_w1, 4 * kDim, a.b1, 2, hbuf)) return 1;
       g_prof.mark(kStMlp1, st);
-      if (token_gemm_bf16(hbuf, F, 4 * kDim, a.tm_w2, kDim, a.b2, 0, delta)) return 1;
+      if (token_gemm_bf16(hbuf, F, 4 * kDim, a.tm_w2, kDim, a.b2, 0, delta_f)) return 1;
       g_prof.mark(kStMlp2, st);
     } else {   // both GEMMs in one kernel on CTA pairs, the hidden activation stays on the SM (ffn_kernel.cuh)
       FfnParams fp{};
       if (make_tmap_rows_bf16(&fp.tmap_x, xn, (uint64_t)F, kDim, kDim, 128, 64)) return fail("tensor map encode failed (feed-forward)");
       fp.tmap_w1 = a.tm_w1_ffn; fp.tmap_w2 = a.tm_w2_ffn;
-      if (make_tmap_out(&fp.tmap_out, delta, (uint64_t)F, kDim, true)) return fail("tensor map encode failed (feed-forward out)");
+      if (make_tmap_out(&fp.tmap_out, delta_f, (uint64_t)F, kDim, true)) return fail("tensor map encode failed (feed-forward out)");
       fp.b1 = a.b1; fp.b2 = a.b2; fp.M = (int)F; fp.pair_tiles = (int)((F + 255) / 256);
       const int grid = 2 * std::min(fp.pair_tiles, persistent_grid() / 2);
       VFP_CUDA(ensure_dynamic_smem(reinterpret_cast<const void*>(ffn_pair_kernel<5>), FfnSmem<5>::kTotal));
@@ -928,8 +930,8 @@ int forward_pass(const vfp_weights* w, const uint8_t* frames_base, int frame_dty
     }
   }
   // close the last block's residual and make the bf16 copy the pooling GEMM reads
-  VFP_CUDA(launch_kernel(add_convert_bf16_kernel, dim3((unsigned)((F * kDim / 8 + 255) / 256)), dim3(256), 0, st, xa, w->n_attn > 0 ? delta : nullptr, xbf,
-                         (long long)(F * kDim / 8)));
+  VFP_CUDA(launch_kernel(add_convert_bf16_kernel, dim3((unsigned)((F * kDim / 8 + 255) / 256)), dim3(256), 0, st, xa, w->n_attn > 0 ? delta : nullptr,
+                         w->n_attn > 0 ? delta_f : nullptr, xbf, (long long)(F * kDim / 8)));
   if (features_out)
     VFP_CUDA(cudaMemcpyAsync(features_out + (size_t)f0 * kDim, xa, (size_t)F * kDim * 4, cudaMemcpyDeviceToDevice, st));
   // ---- pooling + head ----
