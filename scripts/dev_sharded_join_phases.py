@@ -29,7 +29,7 @@ def ev():
     return e
 
 
-for it in range(3):
+for it in range(int(os.environ.get("ITERS", "3"))):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
