@@ -241,16 +241,22 @@ int prep_f32(vfp_weights* w, const float* src, size_t n, float** dev) {
 // forward workspace. Two regions with different granularity:
 //   * the TOKEN region holds one "token pass" (up to all clips of the call): 8.5 KB per frame/token. The token
 //     GEMMs, LayerNorm, attention, pooling and the head each run ONCE per token pass, so their launches are large;
-//   * the CONV region holds the activations of one "conv pass" (kConvPassFrames frames, 112 KB per frame): the
-//     frame encoder walks the token pass in such slices and only leaves the 512 B/frame pooled features behind.
+//   * the CONV region holds the activations of one "conv pass" (up to 65 536 frames by default, 48 KB per frame, plus 64 KB
+//     per frame for 16 384 frames of conv1 output that only the two-kernel stem uses): the frame encoder walks the token
+//     pass in such slices and only leaves the 512 B/frame pooled features behind.
 // ---------------------------------------------------------------------------------------------
-constexpr int64_t kConvPassFrames = 16384;   // workspace is sized for this many frames per conv pass
-// frames actually walked per conv pass (vfp_set_tuning key 3, <= kConvPassFrames): a pass whose c2/c3 activations
-// (48 KB per frame) fit the 126 MB L2 lets conv3 / conv4 read them from L2 instead of HBM
-int64_t g_conv_pass_frames = kConvPassFrames;
+constexpr int64_t kConvPassFrames = 262144;  // workspace is sized for this many frames per conv pass (48 KB per frame)
+constexpr int64_t kStemPassFrames = 16384;   // ... and for this many frames of conv1 output (64 KB per frame, two-kernel stem only)
+// frames actually walked per conv pass (vfp_set_tuning key 3, <= kConvPassFrames). Every launch of the three persistent
+// frame-encoder kernels costs ~13-16 us that do not scale with its size (cluster launch, TMEM allocation, the filters' trip
+// into tensor memory, pipeline ramp and drain), so passes are LARGE: 10 000 x 64-frame clips take 32.9 ms per step with
+// 16 384-frame passes, 32.1 with 65 536 and the same with 131 072 / 262 144 (profiles/r02_conv_pass_sweep.txt). Passes small
+// enough to keep c2 / c3 in the 126 MB L2 (2 048 - 4 096 frames) lose far more to those fixed costs than they save in
+// HBM traffic: 36.3 - 39.4 ms, 35.1 - 36.7 with programmatic dependent launch.
+int64_t g_conv_pass_frames = 65536;
 // conv1+conv2 sub-pass. Measured on B200 (10k x 64-frame clips): 512 -> 71.3 ms/step, 1024 -> 62.9, 2048 -> 60.7,
 // 4096 -> 58.9, 16384 -> 55.8: short L2-sized sub-passes lose more to small launches than they save in HBM traffic.
-int64_t g_stem_pass_frames = kConvPassFrames;
+int64_t g_stem_pass_frames = kStemPassFrames;
 // conv1+conv2 in one kernel (stem_ts_kernel.cuh: conv1's output stays in shared memory as conv2's UMMA operand).
 // Measured on B200 (10k x 64-frame clips): 13.3 ms vs 13.4 + 12.9 ms for the two HBM-bound kernels, so it is the
 // default for u8 / bf16 frames; vfp_set_tuning(1, 0) selects the two-kernel path (always used for fp32 frames).
@@ -302,7 +308,7 @@ TokenWs token_ws_layout(int64_t F, int64_t C) {
   L.total = off;
   return L;
 }
-ConvWs conv_ws_layout(int64_t F) {
+ConvWs conv_ws_layout(int64_t F) {   // F = frames per conv pass
   ConvWs L{};
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -310,14 +316,14 @@ ConvWs conv_ws_layout(int64_t F) {
     off = align_up(off + bytes, 1024);
     return o;
   };
-  L.c1 = take((size_t)F * 32 * 32 * 32 * 2);
+  L.c1 = take((size_t)std::min<int64_t>(F, kStemPassFrames) * 32 * 32 * 32 * 2);
   L.c2 = take((size_t)F * 16 * 16 * 64 * 2);
   L.c3 = take((size_t)F * 8 * 8 * 128 * 2);
   L.total = off;
   return L;
 }
 size_t forward_ws_total(int64_t F, int64_t C) {
-  return token_ws_layout(F, C).total + conv_ws_layout(std::min<int64_t>(F, kConvPassFrames)).total;
+  return token_ws_layout(F, C).total + conv_ws_layout(std::min<int64_t>(F, g_conv_pass_frames)).total;   // follows tuning key 3: size and call under the same setting
 }
 
 // Pipelines of vfp_forward (vfp_set_tuning key 9): token passes are dealt round-robin onto this many internal streams.
@@ -360,7 +366,7 @@ int vfp_device_sm_count(void) {
 }
 
 int vfp_set_tuning(int key, long long value) {
-  if (key == 0 && value >= 64) { g_stem_pass_frames = value; return 0; }
+  if (key == 0 && value >= 64 && value <= kStemPassFrames) { g_stem_pass_frames = value; return 0; }
   if (key == 1 && (value == 0 || value == 2)) { g_fused_stem = (int)value; return 0; }
   if (key == 5 && value >= 0 && value <= 4096) { g_join_prefetch = (int)value; return 0; }
   if (key == 6 && value >= 0 && value <= 4096) { g_topk_prefetch = (int)value; return 0; }
