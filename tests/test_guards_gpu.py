@@ -116,10 +116,21 @@ def test_repeated_runs_are_bit_identical():
     lengths = [int(t) for t in torch.randint(10, 200, (300,), generator=g)]
     frames = torch.randint(0, 256, (sum(lengths), 3, 64, 64), dtype=torch.uint8, generator=g).cuda()
     first = m.fingerprint_packed(frames, lengths).clone()
-    for _ in range(3):
+    for _ in range(8):
         assert torch.equal(m.fingerprint_packed(frames, lengths), first)
     E = first / first.norm(dim=1, keepdim=True)
     a = vfp.threshold_join(E, 0.9)
     b = vfp.threshold_join(E, 0.9)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    # the CTA-pair join over many pair tiles and panels (remote mbarrier arrives between the two CTAs of a pair)
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    big = torch.randn((60_000, 256), generator=gen, device="cuda")
+    big /= big.norm(dim=1, keepdim=True)
+    big[30_000:30_500] = big[:500] + 0.01 * torch.randn((500, 256), generator=gen, device="cuda")
+    big[30_000:30_500] /= big[30_000:30_500].norm(dim=1, keepdim=True)
+    ref = vfp.threshold_join(big, 0.95)
+    assert len(ref[0]) >= 60_000 + 2 * 400
+    for _ in range(4):
+        again = vfp.threshold_join(big, 0.95)
+        assert all(np.array_equal(x, y) for x, y in zip(ref, again))
     assert _native.load().vfp_device_error_word() == 0
