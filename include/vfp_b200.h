@@ -68,7 +68,9 @@ int vfp_weights_embedding_dim(const vfp_weights* w);
 
 /* Device workspace needed to push `frames_per_pass` frames (and up to `clips_per_pass` clips) through
  * the network in one pass. vfp_forward splits its input into passes that fit the workspace it is given;
- * the minimum useful value is the longest clip. */
+ * the minimum useful value is the longest clip. About 9 KB per frame plus the frame encoder's scratch for one conv pass
+ * (48 KB per frame for min(frames_per_pass, 65 536) frames, + 1 GB that only fp32 frames use); the conv-pass size follows
+ * vfp_set_tuning key 3, so size and call under the same setting. */
 size_t vfp_forward_workspace_bytes(int64_t frames_per_pass, int64_t clips_per_pass);
 
 /* Fingerprint `n_clips` clips. `frames` is the packed device tensor (sum T, 3, 64, 64) of type
@@ -165,7 +167,7 @@ int vfp_profile_read(double* stage_ms, int n_stages, uint64_t* launches, int res
 /* Tuning knobs for experiments (process-wide; defaults in parentheses). key 0: frames per conv1+conv2 pass of the two-kernel
  * stem (16384, >= 64); key 1: conv1+conv2 stem: 2 = fused kernel, conv1 as TS-mode tcgen05 UMMA (default for u8 / bf16 frames),
  * 0 = two kernels (always used for fp32 frames); key 2: 1 = hang diagnosis mode (see vfp_debug_hang_log), 0 = watchdog traps
- * (default); key 3: frames per conv pass (64..16384, default 16384); key 5 / key 6: L2 prefetch distance in column tiles of the
+ * (default); key 3: frames per conv pass (64..262144, default 65536); key 5 / key 6: L2 prefetch distance in column tiles of the
  * one-CTA join kernel / the top-k screen for databases larger than L2 (0 = off); key 7: programmatic dependent launch between
  * the forward's kernels (0); key 8: cap on the CTAs of persistent kernels (0 = one per SM); key 9: conv passes in flight on
  * separate streams (1); key 10: join kernel, 0 = one CTA per tile, 1 = A-resident, 2 = A-resident CTA pairs (2); key 11:
