@@ -624,15 +624,16 @@ def run_ours(args):
     known = [k for k in stages if (k in STAGE_FLOPS or k in STAGE_BYTES) and stages[k] > 0]
     dom = max(known, key=lambda k: stages[k])
     sum_stages = sum(stages.values())
-    conv_launches = -(-n_clips * T_FRAMES // 16384)
+    conv_pass = min(65536, n_clips * T_FRAMES)   # the library's default conv pass (vfp_set_tuning key 3)
+    conv_launches = -(-n_clips * T_FRAMES // conv_pass)
     dom_ms = stages[dom]
     tflops = STAGE_FLOPS.get(dom, 0) * n_clips / (dom_ms / 1000.0) / 1e12
     gbs = STAGE_BYTES.get(dom, 0) * n_clips / (dom_ms / 1000.0) / 1e9
     frac_t, frac_h = tflops / peaks["tc_sustained"], gbs / peaks["hbm"]
     hbm_bound = frac_h > frac_t  # the binding roofline is the one the kernel sits closer to
-    # DRAM bytes per launch of the stem from the committed `ncu --set full` capture (profiles/r01_v6_stem_ts_full.txt:
-    # dram__bytes_read.sum + dram__bytes_write.sum of one launch over a 16 384-frame conv pass)
-    ncu_traffic = {"stem_fused": 402.787584e6 + 488.215040e6}
+    # DRAM bytes of the stem from the committed `ncu --set full` capture (profiles/r02_ncu_full_conv_join.txt: dram__bytes_read.sum
+    # + dram__bytes_write.sum = 402.76 + 485.82 MB for a launch over 16 384 frames), scaled to the frames of one launch here
+    ncu_traffic = {"stem_fused": (402.76e6 + 485.82e6) * conv_pass / 16384}
     whole_tfl = value / world * FLOPS_PER_CLIP / 1e12
     roofline = {
         "bound": "hbm" if hbm_bound else "tensor", "kernel": dom,
@@ -640,7 +641,7 @@ def run_ours(args):
         "unit": "GB/s" if hbm_bound else "TFLOP/s", "frac": frac_h if hbm_bound else frac_t,
         "frac_of_burst": None if hbm_bound else tflops / peaks["tc_burst"],
         "traffic": ncu_traffic.get(dom) if (n_clips * T_FRAMES) >= 16384 else None,
-        "traffic_note": "bytes per launch (one 16 384-frame conv pass) from the committed ncu capture of this kernel; algorithmic bytes per launch = %.1f MB" % (STAGE_BYTES.get(dom, 0) / T_FRAMES * 16384 / 1e6),
+        "traffic_note": "bytes per launch (one conv pass of %d frames; ncu capture of a 16 384-frame launch, scaled) ; algorithmic bytes per launch = %.1f MB" % (conv_pass, STAGE_BYTES.get(dom, 0) / T_FRAMES * conv_pass / 1e6),
         "peak_source": f"{peaks['source']} ({'HBM copy bandwidth' if hbm_bound else 'sustained bf16: the kernel is timed inside a long hot loop'})",
         "timing": f"stage events inside a {prof_steps}-step hot loop that follows the timed region (single pipeline): {prof_ms_per_step:.2f} ms/step, sum of stages {sum_stages:.2f} ms",
         "profiled_ms_per_step": prof_ms_per_step, "sum_of_stages_ms": sum_stages, "profile_clocks": prof_clocks,
