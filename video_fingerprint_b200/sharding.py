@@ -105,7 +105,10 @@ def symmetric_block_plan(world: int, rank: int, counts: Sequence[int]) -> List[T
 
 
 class _RowGather:
-    """An all-gather of row shards in flight (NCCL runs it on its own stream): `wait()` returns (rows in rank order, counts)."""
+    """An all-gather of row shards in flight (NCCL runs it on its own stream): `wait()` returns (rows in rank order, counts).
+    The returned rows live in a buffer the next gather of the same shape overwrites: use them before starting another one."""
+
+    _bufs: dict = {}
 
     def __init__(self, local: torch.Tensor, group=None):
         world, _ = _world(group)
@@ -123,7 +126,15 @@ class _RowGather:
         else:
             padded = torch.zeros((self.width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
             padded[: local.shape[0]] = local
-        self.buf = torch.empty((world * self.width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        # One receive buffer per (device, dtype, shape) is kept and reused: a fresh 0.5 - 1 GB allocation per call means a fresh
+        # address for NCCL every time (and allocator churn); on shared 2-GPU boxes that showed up as sporadic ~80 ms stalls.
+        # The collective is ordered after the current stream's work, i.e. after the previous call's reads of the buffer.
+        shape = (world * self.width,) + tuple(local.shape[1:])
+        key = (str(local.device), local.dtype, shape)
+        self.buf = _RowGather._bufs.get(key)
+        if self.buf is None:
+            _RowGather._bufs.clear()   # keep one buffer alive, not one per size ever seen
+            self.buf = _RowGather._bufs[key] = torch.empty(shape, dtype=local.dtype, device=local.device)
         self.work = dist.all_gather_into_tensor(self.buf, padded, group=group, async_op=True)
 
     def wait(self) -> Tuple[torch.Tensor, List[int]]:
