@@ -9,13 +9,16 @@ pass of `model.fingerprint_packed` over all clips of the rank. Launched under to
 sharded, no data-path collective in the forward => weak scaling).
 
 One JSON line on stdout (rank 0):
-  value        whole-job videos/s, device-resident inputs, product defaults (two token passes in flight, PDL)
+  value        whole-job videos/s, device-resident inputs, product defaults (one pipeline, 65 536-frame conv passes); CUDA events
+               around exactly K steps after W warm-up steps, max over ranks
   e2e          the same metric through the public API `model.fingerprint_host` with HOST (pinned) uint8 frames,
                host<->device copies inside the timed region
   roofline     dominant kernel, from per-stage CUDA-event times taken INSIDE a hot multi-step loop (library stage
                profiler, single pipeline so that stages do not overlap); sum of stages is printed beside that loop's step time
   cpu_baseline the oracle's reference-semantics B=1 loop on the box's host cores (N = 1 only)
-  join         all-pairs cosine threshold join, 262 144 rows per GPU (weak scaling; second half of the BASELINE metric)
+  join         all-pairs cosine threshold join, 262 144 rows per GPU (weak scaling; second half of the BASELINE metric). The
+               sharded joins (this and cfg4) synchronise with the host several times per call: warm-up until two calls agree
+               within 10 %, then the MEDIAN of five calls (max over ranks each); mean, per-call and warm-up lists are printed
   cfg3_varlen  BASELINE configs[2]: 10 000 clips of 16-300 frames (+ a few > 500-frame inputs through subsample()),
                LPT-sharded over the ranks, uint8 frames in HBM, parity spot-check against the oracle inside the run
   cfg4_join    BASELINE configs[3]: 1 048 576 rows in total, row-block sharded, NCCL all-gather overlapped with the
