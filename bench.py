@@ -261,6 +261,8 @@ def run_reference(args):
     torch.set_num_threads(os.cpu_count() or 1)  # torchrun pins OMP_NUM_THREADS=1; the reference arm gets every host core
     threads = torch.get_num_threads()
     per_step = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    if args.ref_budget:   # tests: a shorter bounded sample per step
+        per_step = args.ref_budget
     for _ in range(args.warmup):
         cpu_reference_rate(per_step / 4, 64)
     clips, secs = 0, 0.0
@@ -717,6 +719,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-join", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=0.0, help="reference arm: seconds of CPU work per step (default: 4-20 s from --steps)")
     ap.add_argument("--no-cfg3", action="store_true")
     ap.add_argument("--no-cfg4", action="store_true")
     ap.add_argument("--no-cfg5", action="store_true")

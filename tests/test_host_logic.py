@@ -157,3 +157,21 @@ def test_symmetric_block_plan_covers_every_ordered_pair_once(counts):
             cover[starts[rank] + q_lo : starts[rank] + q_hi, c_lo:c_hi] += 1
             cover[c_lo:c_hi, starts[rank] + q_lo : starts[rank] + q_hi] += 1     # the mirrored pairs
     assert np.all(cover == 1)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver runs it before our arm) times the oracle port on the host cores and prints
+    one JSON line with the keys the contract names; no GPU, no extension needed."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-budget", "1.5"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["unit"] == "videos/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
+    assert line["e2e"] == {"value": line["value"], "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["gpu_launches"] == 0 and line["steps"] == 1 and line["warmup"] == 0
